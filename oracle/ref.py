@@ -1,0 +1,275 @@
+"""ctypes binding of oracle/_ref/libaclref.so -- the UNMODIFIED reference compiled from /root/reference.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's CPU baseline /
+`--impl reference` legs. The product package (acl_b200/) never imports this module.
+
+The library is built by oracle/Makefile (see oracle/ref_tool.cpp). On the GPU box the prebuilt .so
+travels with the repository snapshot; /root/reference is never read at run time.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field, asdict
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_ref", "libaclref.so")
+
+# acl::rotation_format8 / vector_format8 (core/track_formats.h)
+QUATF_FULL, QUATF_DROP_W_FULL, QUATF_DROP_W_VARIABLE = 0, 2, 3
+VECTOR3F_FULL, VECTOR3F_VARIABLE = 0, 1
+# acl::compression_level8 (compression/compression_level.h)
+LEVEL_LOWEST, LEVEL_LOW, LEVEL_MEDIUM, LEVEL_HIGH, LEVEL_HIGHEST, LEVEL_AUTOMATIC = 0, 1, 2, 3, 4, 100
+# acl::sample_rounding_policy (core/sample_rounding_policy.h)
+ROUND_NONE, ROUND_FLOOR, ROUND_CEIL, ROUND_NEAREST, ROUND_PER_TRACK = 0, 1, 2, 3, 4
+# acl::sample_looping_policy (core/sample_looping_policy.h)
+LOOP_CLAMP, LOOP_WRAP, LOOP_AS_COMPRESSED = 0, 1, 2
+# acl::track_type8 (core/track_types.h)
+TRACK_FLOAT1F, TRACK_FLOAT2F, TRACK_FLOAT3F, TRACK_FLOAT4F, TRACK_VECTOR4F, TRACK_QVVF = 0, 1, 2, 3, 4, 12
+
+# settings kinds understood by ref_tool.cpp
+SETTINGS_DEFAULT, SETTINGS_DEBUG, SETTINGS_BENCHMARK, SETTINGS_NEVER, SETTINGS_ALL_LERP, SETTINGS_RAW_ONLY = 0, 1, 2, 3, 4, 5
+# writer modes understood by ref_tool.cpp
+WRITER_LEGACY, WRITER_SKIPPED, WRITER_CONSTANT, WRITER_VARIABLE = 0, 1, 2, 3
+
+
+class _TransformSpec(C.Structure):
+    _fields_ = [
+        ("num_tracks", C.c_uint32), ("num_samples", C.c_uint32), ("sample_rate", C.c_float), ("seed", C.c_uint32),
+        ("rot_default_pct", C.c_uint32), ("rot_constant_pct", C.c_uint32),
+        ("trans_default_pct", C.c_uint32), ("trans_constant_pct", C.c_uint32),
+        ("scale_default_pct", C.c_uint32), ("scale_constant_pct", C.c_uint32),
+        ("partial_activity_pct", C.c_uint32), ("noisy_pct", C.c_uint32), ("looping_content", C.c_uint32),
+        ("translation_range", C.c_float), ("precision", C.c_float), ("shell_distance", C.c_float),
+        ("rotation_format", C.c_uint32), ("translation_format", C.c_uint32), ("scale_format", C.c_uint32),
+        ("level", C.c_uint32), ("optimize_loops", C.c_uint32), ("strip_trivial", C.c_uint32),
+        ("strip_proportion", C.c_float), ("strip_threshold", C.c_float),
+    ]
+
+
+class _ScalarSpec(C.Structure):
+    _fields_ = [
+        ("num_tracks", C.c_uint32), ("num_samples", C.c_uint32), ("sample_rate", C.c_float), ("seed", C.c_uint32),
+        ("track_type", C.c_uint32), ("constant_pct", C.c_uint32), ("noisy_pct", C.c_uint32), ("precision", C.c_float),
+    ]
+
+
+class SeekInfo(C.Structure):
+    _fields_ = [
+        ("sample_time", C.c_float), ("interpolation_alpha", C.c_float),
+        ("key_frame_bit_offsets", C.c_uint32 * 2), ("segment_offsets", C.c_uint32 * 2),
+        ("format_offsets", C.c_uint32 * 2), ("range_offsets", C.c_uint32 * 2), ("animated_offsets", C.c_uint32 * 2),
+        ("uses_single_segment", C.c_uint32), ("clip_duration", C.c_float), ("looping_policy", C.c_uint32),
+    ]
+
+
+@dataclass
+class TransformSpec:
+    """Synthetic clip recipe: the default values are the humanoid of config C2."""
+    num_tracks: int = 100
+    num_samples: int = 60
+    sample_rate: float = 30.0
+    seed: int = 2000
+    rot_default_pct: int = 0
+    rot_constant_pct: int = 0
+    trans_default_pct: int = 0
+    trans_constant_pct: int = 90
+    scale_default_pct: int = 100
+    scale_constant_pct: int = 0
+    partial_activity_pct: int = 0
+    noisy_pct: int = 0
+    looping_content: int = 0
+    translation_range: float = 10.0
+    precision: float = 0.01
+    shell_distance: float = 3.0
+    rotation_format: int = QUATF_DROP_W_VARIABLE
+    translation_format: int = VECTOR3F_VARIABLE
+    scale_format: int = VECTOR3F_VARIABLE
+    level: int = LEVEL_AUTOMATIC
+    optimize_loops: int = 1
+    strip_trivial: int = 1
+    strip_proportion: float = 0.0
+    strip_threshold: float = 0.0
+
+    def to_c(self) -> _TransformSpec:
+        return _TransformSpec(**asdict(self))
+
+
+@dataclass
+class ScalarSpec:
+    num_tracks: int = 4096
+    num_samples: int = 1024
+    sample_rate: float = 30.0
+    seed: int = 42
+    track_type: int = TRACK_FLOAT1F
+    constant_pct: int = 12
+    noisy_pct: int = 0
+    precision: float = 0.001
+
+    def to_c(self) -> _ScalarSpec:
+        return _ScalarSpec(**asdict(self))
+
+
+_lib = None
+
+
+def available() -> bool:
+    return os.path.exists(_LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError(f"{_LIB_PATH} is missing: run `make -C oracle` where /root/reference exists")
+        l = C.CDLL(_LIB_PATH)
+        l.aclref_version.restype = C.c_char_p
+        l.aclref_hardware_threads.restype = C.c_uint32
+        l.aclref_compress_transform.argtypes = [C.POINTER(_TransformSpec), C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]
+        l.aclref_compress_scalar.argtypes = [C.POINTER(_ScalarSpec), C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]
+        l.aclref_free.argtypes = [C.c_void_p]
+        l.aclref_is_valid.argtypes = [C.c_void_p, C.c_uint32]
+        l.aclref_decompress_tracks.argtypes = [C.c_void_p, C.c_float, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.aclref_decompress_track.argtypes = [C.c_void_p, C.c_float, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.aclref_scalar_decompress.argtypes = [C.c_void_p, C.c_float, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32,
+                                               C.c_void_p, C.c_void_p]
+        l.aclref_seek_info_transform.argtypes = [C.c_void_p, C.c_float, C.c_uint32, C.c_uint32, C.POINTER(SeekInfo)]
+        for name in ("aclref_bench_transform", "aclref_bench_scalar"):
+            fn = getattr(l, name)
+            fn.restype = C.c_double
+            fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        l.aclref_compress_transform_batch.restype = C.c_uint64
+        l.aclref_compress_transform_batch.argtypes = [C.POINTER(_TransformSpec), C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64,
+                                                      C.c_void_p, C.c_void_p]
+        _lib = l
+    return _lib
+
+
+def aligned_blob(data: bytes | np.ndarray, slack: int = 64) -> np.ndarray:
+    """Copy a blob into a 64-byte aligned uint8 array with `slack` zero bytes after it (the reference's
+    `_unsafe` unpackers read up to 15 bytes past the bit stream, compress.transform.impl.h:387-396)."""
+    src = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+    raw = np.zeros(src.size + slack + 64, dtype=np.uint8)
+    shift = (-raw.ctypes.data) % 64
+    out = raw[shift:shift + src.size + slack]
+    out[:src.size] = src
+    return out[:src.size]
+
+
+def _take(ptr: C.c_void_p, size: int) -> np.ndarray:
+    buf = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(size,))
+    out = aligned_blob(buf.copy())
+    lib().aclref_free(ptr)
+    return out
+
+
+def compress_transform(spec: TransformSpec) -> np.ndarray:
+    """Synthesise + compress one transform clip with the reference compressor. Returns the blob bytes."""
+    c_spec = spec.to_c()
+    ptr, size = C.c_void_p(), C.c_uint32()
+    rc = lib().aclref_compress_transform(C.byref(c_spec), C.byref(ptr), C.byref(size))
+    if rc != 0:
+        raise RuntimeError(f"reference compression failed ({rc}) for {spec}")
+    return _take(ptr, size.value)
+
+
+def compress_scalar(spec: ScalarSpec) -> np.ndarray:
+    c_spec = spec.to_c()
+    ptr, size = C.c_void_p(), C.c_uint32()
+    rc = lib().aclref_compress_scalar(C.byref(c_spec), C.byref(ptr), C.byref(size))
+    if rc != 0:
+        raise RuntimeError(f"reference compression failed ({rc}) for {spec}")
+    return _take(ptr, size.value)
+
+
+def compress_transform_batch(spec: TransformSpec, num_clips: int, num_threads: int = 0, bytes_per_clip_hint: int = 0):
+    """Compress `num_clips` clips (seed, seed+1, ...) on `num_threads` host threads.
+    Returns (buffer uint8[...], offsets uint64[num_clips], sizes uint32[num_clips]); every blob starts on a
+    64 byte boundary inside `buffer`."""
+    if bytes_per_clip_hint <= 0:
+        probe = compress_transform(spec)
+        bytes_per_clip_hint = int(probe.size * 1.5) + 256
+    capacity = num_clips * bytes_per_clip_hint + 4096
+    raw = np.zeros(capacity + 64, dtype=np.uint8)
+    shift = (-raw.ctypes.data) % 64
+    buffer = raw[shift:shift + capacity]
+    offsets = np.zeros(num_clips, dtype=np.uint64)
+    sizes = np.zeros(num_clips, dtype=np.uint32)
+    c_spec = spec.to_c()
+    used = lib().aclref_compress_transform_batch(C.byref(c_spec), num_clips, num_threads, buffer.ctypes.data, capacity,
+                                                 offsets.ctypes.data, sizes.ctypes.data)
+    if used == 0:
+        raise RuntimeError("reference batch compression failed (or the size hint was too small)")
+    return buffer[:used], offsets, sizes
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def num_tracks_of(blob: np.ndarray) -> int:
+    return int(blob[16:20].view(np.uint32)[0])
+
+
+def decompress_tracks(blob: np.ndarray, t: float, rounding: int = ROUND_NONE, looping: int = LOOP_AS_COMPRESSED,
+                      settings: int = SETTINGS_DEFAULT, writer: int = WRITER_LEGACY,
+                      per_track_rounding: np.ndarray | None = None, constant_defaults: np.ndarray | None = None,
+                      variable_defaults: np.ndarray | None = None, out: np.ndarray | None = None) -> np.ndarray:
+    """Reference seek(t, rounding) + decompress_tracks(writer). Returns float32 [num_tracks, 12]
+    (rotation xyzw, translation xyz + pad, scale xyz + pad). `out` lets the caller pre-fill the pose (skipped mode)."""
+    n = num_tracks_of(blob)
+    if out is None:
+        out = np.zeros((n, 12), dtype=np.float32)
+    rc = lib().aclref_decompress_tracks(blob.ctypes.data, t, rounding, looping, settings, writer,
+                                        _ptr(per_track_rounding), _ptr(constant_defaults), _ptr(variable_defaults), out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"reference decompress_tracks failed ({rc})")
+    return out
+
+
+def decompress_track(blob: np.ndarray, t: float, track_index: int, rounding: int = ROUND_NONE, looping: int = LOOP_AS_COMPRESSED,
+                     settings: int = SETTINGS_DEFAULT, writer: int = WRITER_LEGACY,
+                     per_track_rounding: np.ndarray | None = None, constant_defaults: np.ndarray | None = None,
+                     variable_defaults: np.ndarray | None = None, out: np.ndarray | None = None) -> np.ndarray:
+    n = num_tracks_of(blob)
+    if out is None:
+        out = np.zeros((n, 12), dtype=np.float32)
+    rc = lib().aclref_decompress_track(blob.ctypes.data, t, rounding, looping, settings, writer, track_index,
+                                       _ptr(per_track_rounding), _ptr(constant_defaults), _ptr(variable_defaults), out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"reference decompress_track failed ({rc})")
+    return out
+
+
+def scalar_decompress(blob: np.ndarray, t: float, rounding: int = ROUND_NONE, looping: int = LOOP_AS_COMPRESSED,
+                      settings: int = 0, track_index: int = -1, per_track_rounding: np.ndarray | None = None) -> np.ndarray:
+    """Reference scalar decompress_tracks (track_index < 0) or decompress_track. Returns float32 [num_tracks, 4]."""
+    n = num_tracks_of(blob)
+    out = np.zeros((n, 4), dtype=np.float32)
+    rc = lib().aclref_scalar_decompress(blob.ctypes.data, t, rounding, looping, settings, track_index, _ptr(per_track_rounding), out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"reference scalar decompress failed ({rc})")
+    return out
+
+
+def seek_info(blob: np.ndarray, t: float, rounding: int = ROUND_NONE, looping: int = LOOP_AS_COMPRESSED) -> SeekInfo:
+    info = SeekInfo()
+    rc = lib().aclref_seek_info_transform(blob.ctypes.data, t, rounding, looping, C.byref(info))
+    if rc != 0:
+        raise RuntimeError("reference seek_info failed")
+    return info
+
+
+def bench(blobs: list[np.ndarray], request_clip: np.ndarray, request_time: np.ndarray, max_tracks: int,
+          num_threads: int, repeats: int = 1, scalar: bool = False) -> float:
+    """Seconds taken by the reference CPU path (fastest of `repeats` passes) for the request list."""
+    ptrs = (C.c_void_p * len(blobs))(*[b.ctypes.data for b in blobs])
+    request_clip = np.ascontiguousarray(request_clip, dtype=np.uint32)
+    request_time = np.ascontiguousarray(request_time, dtype=np.float32)
+    fn = lib().aclref_bench_scalar if scalar else lib().aclref_bench_transform
+    return float(fn(C.cast(ptrs, C.c_void_p), request_clip.ctypes.data, request_time.ctypes.data, request_clip.size,
+                    max_tracks, num_threads, repeats, None))
