@@ -1,0 +1,382 @@
+// acl_b200/csrc/api.cpp -- the extern "C" surface declared in include/aclb200.h.
+#include "context.h"
+
+#include <cstring>
+#include <functional>
+#include <new>
+
+namespace aclb200
+{
+	aclb200_status build_clipset(aclb200_context* context, const std::function<const uint8_t*(uint32_t)>& get_blob, const uint32_t* sizes,
+		uint32_t num_clips, bool check_hash, aclb200_clipset** out_clipset, uint32_t* out_failed_clip);
+	void plan_launch(DecodeParams& params);
+
+	namespace
+	{
+		uint32_t scalar_components(uint32_t track_type)
+		{
+			return track_type <= 3 ? track_type + 1 : 4;
+		}
+
+		aclb200_status make_params(aclb200_context* context, const aclb200_clipset* clipset, const aclb200_request* d_requests,
+			uint32_t num_requests, const aclb200_options* options, void* d_out, bool want_transform, bool single_track, DecodeParams& params)
+		{
+			if (context == nullptr || clipset == nullptr || options == nullptr)
+				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "null context / clipset / options");
+			if (options->struct_size != sizeof(aclb200_options))
+				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "options.struct_size does not match this library, call aclb200_default_options()");
+			if (num_requests != 0 && (d_requests == nullptr || d_out == nullptr))
+				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "null request / output pointer");
+			if (clipset->device != context->device)
+				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "clip set lives on another device");
+			const bool is_transform = clipset->info.track_type == ACLB200_TRACK_QVVF;
+			if (is_transform != want_transform)
+				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, want_transform ? "not a transform clip set" : "not a scalar clip set");
+			if (options->rounding_policy > ACLB200_ROUND_PER_TRACK || options->looping_policy > ACLB200_LOOP_AS_COMPRESSED
+				|| options->normalization > ACLB200_NORMALIZE_ALWAYS || options->output_layout > ACLB200_LAYOUT_QVV40
+				|| options->default_rotation_mode > ACLB200_DEFAULT_VARIABLE || options->default_translation_mode > ACLB200_DEFAULT_VARIABLE
+				|| options->default_scale_mode > ACLB200_DEFAULT_LEGACY)
+				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "option value out of range");
+			// ACL_ASSERT(rounding_policy != per_track || is_per_track_rounding_supported()), decompress.impl.h:211
+			if (options->rounding_policy == ACLB200_ROUND_PER_TRACK && !options->per_track_rounding)
+				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "per track rounding must be enabled to seek with the per_track policy");
+
+			std::memset(&params, 0, sizeof(params));
+			params.blobs = clipset->d_blobs;
+			params.index = clipset->d_index;
+			params.clips = clipset->d_clips;
+			params.requests = d_requests;
+			params.num_requests = num_requests;
+			params.num_clips = clipset->info.num_clips;
+			params.max_tracks = clipset->info.max_tracks;
+			params.out = static_cast<uint8_t*>(d_out);
+			if (is_transform)
+				params.bone_stride = options->output_layout == ACLB200_LAYOUT_QVV48 ? 48u : 40u;
+			else
+				params.bone_stride = scalar_components(clipset->info.track_type) * 4u;
+			params.pose_stride = options->pose_stride_bytes != 0 ? options->pose_stride_bytes : uint64_t(params.max_tracks) * params.bone_stride;
+			if (!single_track && params.pose_stride < uint64_t(params.max_tracks) * params.bone_stride)
+				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "pose_stride_bytes is smaller than one pose");
+			if (is_transform && (params.pose_stride % (options->output_layout == ACLB200_LAYOUT_QVV48 ? 16 : 8)) != 0)
+				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "pose_stride_bytes must keep bones 16 (QVV48) / 8 (QVV40) byte aligned");
+			params.rounding_policy = options->rounding_policy;
+			params.looping_policy = options->looping_policy;
+			params.normalization = options->normalization;
+			params.per_track_rounding = options->per_track_rounding != 0;
+			params.wrapping = options->wrapping != 0;
+			params.clamp_sample_time = options->clamp_sample_time != 0;
+			params.multiple_rotation_formats = options->multiple_rotation_formats != 0;
+			params.default_mode[0] = options->default_rotation_mode;
+			params.default_mode[1] = options->default_translation_mode;
+			params.default_mode[2] = options->default_scale_mode;
+			std::memcpy(params.constant_defaults, options->constant_defaults, sizeof(params.constant_defaults));
+			params.variable_defaults = options->d_variable_defaults;
+			params.per_track_policies = options->d_per_track_rounding;
+			params.layout = options->output_layout;
+			plan_launch(params);
+			return ACLB200_OK;
+		}
+
+		aclb200_status finish_launch(aclb200_context* context, cudaError_t error, const char* what)
+		{
+			if (error == cudaSuccess)
+				context->launch_count++;
+			return check_cuda(context, error, what);
+		}
+	}
+}
+
+using namespace aclb200;
+
+extern "C"
+{
+	const char* aclb200_version_string(void)
+	{
+		return "aclb200 0.1 (sm_100a; ACL compressed_tracks v02_00_00..v02_01_00)";
+	}
+
+	const char* aclb200_status_string(aclb200_status status)
+	{
+		switch (status)
+		{
+		case ACLB200_OK: return "ok";
+		case ACLB200_ERR_INVALID_ARGUMENT: return "invalid argument";
+		case ACLB200_ERR_INVALID_CLIP: return "invalid compressed_tracks buffer";
+		case ACLB200_ERR_UNSUPPORTED: return "unsupported clip";
+		case ACLB200_ERR_NO_DEVICE: return "no CUDA device";
+		case ACLB200_ERR_CUDA: return "CUDA error";
+		case ACLB200_ERR_OUT_OF_MEMORY: return "out of device memory";
+		default: return "unknown status";
+		}
+	}
+
+	void aclb200_default_options(aclb200_options* options)
+	{
+		if (options == nullptr)
+			return;
+		std::memset(options, 0, sizeof(*options));
+		options->struct_size = sizeof(aclb200_options);
+		options->rounding_policy = ACLB200_ROUND_NONE;
+		options->looping_policy = ACLB200_LOOP_AS_COMPRESSED;
+		options->normalization = ACLB200_NORMALIZE_LERP_ONLY;		// default_transform_decompression_settings, decompression_settings.h:226
+		options->per_track_rounding = 0;							// :231
+		options->wrapping = 1;										// :153
+		options->clamp_sample_time = 1;								// :80
+		options->multiple_rotation_formats = 0;						// :219
+		options->default_rotation_mode = ACLB200_DEFAULT_CONSTANT;	// track_writer.h:170-172
+		options->default_translation_mode = ACLB200_DEFAULT_CONSTANT;
+		options->default_scale_mode = ACLB200_DEFAULT_LEGACY;
+		options->constant_defaults[3] = 1.0f;						// :174-176
+		options->constant_defaults[8] = options->constant_defaults[9] = options->constant_defaults[10] = 1.0f;
+		options->output_layout = ACLB200_LAYOUT_QVV48;
+		options->math_mode = ACLB200_MATH_EXACT;
+	}
+
+	aclb200_status aclb200_create(int device, aclb200_context** out_context)
+	{
+		if (out_context == nullptr)
+			return ACLB200_ERR_INVALID_ARGUMENT;
+		*out_context = nullptr;
+		int device_count = 0;
+		if (cudaGetDeviceCount(&device_count) != cudaSuccess || device_count == 0)
+			return ACLB200_ERR_NO_DEVICE;		// no CPU fallback exists
+		if (device < 0 || device >= device_count)
+			return ACLB200_ERR_INVALID_ARGUMENT;
+		cudaDeviceProp prop;
+		if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+			return ACLB200_ERR_CUDA;
+
+		aclb200_context* context = new (std::nothrow) aclb200_context();
+		if (context == nullptr)
+			return ACLB200_ERR_OUT_OF_MEMORY;
+		context->device = device;
+		context->num_sms = prop.multiProcessorCount;
+		if (prop.major < 10)
+		{
+			// the kernels are compiled for sm_100a only
+			delete context;
+			return ACLB200_ERR_NO_DEVICE;
+		}
+		*out_context = context;
+		return ACLB200_OK;
+	}
+
+	void aclb200_destroy(aclb200_context* context)
+	{
+		if (context == nullptr)
+			return;
+		cudaSetDevice(context->device);
+		cudaFree(context->d_scratch_requests);
+		cudaFree(context->d_scratch_out);
+		if (context->host_stream != nullptr)
+			cudaStreamDestroy(context->host_stream);
+		delete context;
+	}
+
+	const char* aclb200_last_error(const aclb200_context* context)
+	{
+		return context != nullptr ? context->last_error.c_str() : "null context";
+	}
+
+	aclb200_status aclb200_upload_clips(aclb200_context* context, const void* const* blobs, const uint32_t* sizes, uint32_t num_clips,
+		uint32_t check_hash, aclb200_clipset** out_clipset, uint32_t* out_failed_clip)
+	{
+		if (blobs == nullptr)
+			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "upload_clips: null blob array");
+		return build_clipset(context, [blobs](uint32_t clip) { return static_cast<const uint8_t*>(blobs[clip]); }, sizes, num_clips,
+			check_hash != 0, out_clipset, out_failed_clip);
+	}
+
+	aclb200_status aclb200_upload_clips_packed(aclb200_context* context, const void* buffer, const uint64_t* offsets, const uint32_t* sizes,
+		uint32_t num_clips, uint32_t check_hash, aclb200_clipset** out_clipset, uint32_t* out_failed_clip)
+	{
+		if (buffer == nullptr || offsets == nullptr)
+			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "upload_clips_packed: null buffer / offsets");
+		const uint8_t* base = static_cast<const uint8_t*>(buffer);
+		return build_clipset(context, [base, offsets](uint32_t clip) { return base + offsets[clip]; }, sizes, num_clips,
+			check_hash != 0, out_clipset, out_failed_clip);
+	}
+
+	void aclb200_release_clipset(aclb200_context* context, aclb200_clipset* clipset)
+	{
+		if (clipset == nullptr)
+			return;
+		cudaSetDevice(clipset->device);
+		cudaFree(clipset->d_blobs);
+		cudaFree(clipset->d_index);
+		cudaFree(clipset->d_clips);
+		delete clipset;
+		(void)context;
+	}
+
+	aclb200_status aclb200_clipset_get_info(const aclb200_clipset* clipset, aclb200_clipset_info* out_info)
+	{
+		if (clipset == nullptr || out_info == nullptr)
+			return ACLB200_ERR_INVALID_ARGUMENT;
+		*out_info = clipset->info;
+		return ACLB200_OK;
+	}
+
+	aclb200_status aclb200_clipset_get_clip_info(const aclb200_clipset* clipset, uint32_t clip, aclb200_clip_info* out_info)
+	{
+		if (clipset == nullptr || out_info == nullptr || clip >= clipset->info.num_clips)
+			return ACLB200_ERR_INVALID_ARGUMENT;
+		const ClipDesc& desc = clipset->host_clips[clip];
+		out_info->num_tracks = desc.num_tracks;
+		out_info->num_samples = desc.num_samples;
+		out_info->sample_rate = desc.sample_rate;
+		out_info->looping_policy = clipset->host_looping[clip];
+		out_info->duration = out_info->looping_policy == ACLB200_LOOP_WRAP ? desc.duration_wrap : desc.duration_clamp;
+		out_info->num_segments = desc.num_segments;
+		out_info->hash = desc.hash;
+		out_info->size = desc.size;
+		return ACLB200_OK;
+	}
+
+	aclb200_status aclb200_decompress_tracks(aclb200_context* context, const aclb200_clipset* clipset,
+		const aclb200_request* d_requests, uint32_t num_requests, const aclb200_options* options, void* d_out, void* stream)
+	{
+		DecodeParams params;
+		const aclb200_status status = make_params(context, clipset, d_requests, num_requests, options, d_out, true, false, params);
+		if (status != ACLB200_OK || num_requests == 0)
+			return status;
+		cudaSetDevice(context->device);
+		return finish_launch(context, launch_transform_decompress_tracks(params, options->math_mode, static_cast<cudaStream_t>(stream)), "decompress_tracks");
+	}
+
+	aclb200_status aclb200_decompress_track(aclb200_context* context, const aclb200_clipset* clipset,
+		const aclb200_request* d_requests, const uint32_t* d_track_indices, uint32_t num_requests,
+		const aclb200_options* options, void* d_out, void* stream)
+	{
+		DecodeParams params;
+		const aclb200_status status = make_params(context, clipset, d_requests, num_requests, options, d_out, true, true, params);
+		if (status != ACLB200_OK || num_requests == 0)
+			return status;
+		if (d_track_indices == nullptr)
+			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "null track index pointer");
+		params.track_indices = d_track_indices;
+		cudaSetDevice(context->device);
+		return finish_launch(context, launch_transform_decompress_track(params, options->math_mode, static_cast<cudaStream_t>(stream)), "decompress_track");
+	}
+
+	aclb200_status aclb200_scalar_decompress_tracks(aclb200_context* context, const aclb200_clipset* clipset,
+		const aclb200_request* d_requests, uint32_t num_requests, const aclb200_options* options, void* d_out, void* stream)
+	{
+		DecodeParams params;
+		const aclb200_status status = make_params(context, clipset, d_requests, num_requests, options, d_out, false, false, params);
+		if (status != ACLB200_OK || num_requests == 0)
+			return status;
+		cudaSetDevice(context->device);
+		return finish_launch(context, launch_scalar_decompress_tracks(params, static_cast<cudaStream_t>(stream)), "scalar_decompress_tracks");
+	}
+
+	aclb200_status aclb200_scalar_decompress_track(aclb200_context* context, const aclb200_clipset* clipset,
+		const aclb200_request* d_requests, const uint32_t* d_track_indices, uint32_t num_requests,
+		const aclb200_options* options, void* d_out, void* stream)
+	{
+		DecodeParams params;
+		const aclb200_status status = make_params(context, clipset, d_requests, num_requests, options, d_out, false, true, params);
+		if (status != ACLB200_OK || num_requests == 0)
+			return status;
+		if (d_track_indices == nullptr)
+			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "null track index pointer");
+		params.track_indices = d_track_indices;
+		cudaSetDevice(context->device);
+		return finish_launch(context, launch_scalar_decompress_track(params, static_cast<cudaStream_t>(stream)), "scalar_decompress_track");
+	}
+
+	aclb200_status aclb200_decompress_tracks_host(aclb200_context* context, const aclb200_clipset* clipset,
+		const aclb200_request* requests, uint32_t num_requests, const aclb200_options* options, void* out, size_t out_bytes)
+	{
+		if (context == nullptr || clipset == nullptr || options == nullptr)
+			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "null context / clipset / options");
+		if (num_requests == 0)
+			return ACLB200_OK;
+		if (requests == nullptr || out == nullptr)
+			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "null request / output pointer");
+
+		const bool is_transform = clipset->info.track_type == ACLB200_TRACK_QVVF;
+		const uint32_t bone_stride = is_transform ? (options->output_layout == ACLB200_LAYOUT_QVV48 ? 48u : 40u) : scalar_components(clipset->info.track_type) * 4u;
+		const uint64_t pose_stride = options->pose_stride_bytes != 0 ? options->pose_stride_bytes : uint64_t(clipset->info.max_tracks) * bone_stride;
+		const size_t needed_out = size_t(pose_stride) * num_requests;
+		if (out_bytes < needed_out)
+			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "output buffer too small");
+		const size_t needed_requests = sizeof(aclb200_request) * size_t(num_requests);
+
+		cudaError_t error = cudaSetDevice(context->device);
+		if (error == cudaSuccess && context->host_stream == nullptr)
+			error = cudaStreamCreateWithFlags(&context->host_stream, cudaStreamNonBlocking);
+		if (error == cudaSuccess && context->scratch_requests_bytes < needed_requests)
+		{
+			cudaFree(context->d_scratch_requests);
+			context->d_scratch_requests = nullptr;
+			context->scratch_requests_bytes = 0;
+			error = cudaMalloc(&context->d_scratch_requests, needed_requests);
+			if (error == cudaSuccess) context->scratch_requests_bytes = needed_requests;
+		}
+		if (error == cudaSuccess && context->scratch_out_bytes < needed_out)
+		{
+			cudaFree(context->d_scratch_out);
+			context->d_scratch_out = nullptr;
+			context->scratch_out_bytes = 0;
+			error = cudaMalloc(&context->d_scratch_out, needed_out);
+			if (error == cudaSuccess) context->scratch_out_bytes = needed_out;
+		}
+		if (error != cudaSuccess)
+			return check_cuda(context, error, "decompress_tracks_host: scratch allocation");
+
+		cudaStream_t stream = context->host_stream;
+		// `skipped` default sub-tracks keep what the caller's buffer held: bring the buffer in first in that case
+		const bool keeps_input = is_transform && (options->default_rotation_mode == ACLB200_DEFAULT_SKIPPED
+			|| options->default_translation_mode == ACLB200_DEFAULT_SKIPPED || options->default_scale_mode == ACLB200_DEFAULT_SKIPPED);
+		error = cudaMemcpyAsync(context->d_scratch_requests, requests, needed_requests, cudaMemcpyHostToDevice, stream);
+		if (error == cudaSuccess && keeps_input)
+			error = cudaMemcpyAsync(context->d_scratch_out, out, needed_out, cudaMemcpyHostToDevice, stream);
+		if (error != cudaSuccess)
+			return check_cuda(context, error, "decompress_tracks_host: upload");
+
+		const aclb200_request* d_requests = static_cast<const aclb200_request*>(context->d_scratch_requests);
+		const aclb200_status status = is_transform
+			? aclb200_decompress_tracks(context, clipset, d_requests, num_requests, options, context->d_scratch_out, stream)
+			: aclb200_scalar_decompress_tracks(context, clipset, d_requests, num_requests, options, context->d_scratch_out, stream);
+		if (status != ACLB200_OK)
+			return status;
+
+		error = cudaMemcpyAsync(out, context->d_scratch_out, needed_out, cudaMemcpyDeviceToHost, stream);
+		if (error == cudaSuccess)
+			error = cudaStreamSynchronize(stream);
+		return check_cuda(context, error, "decompress_tracks_host: download");
+	}
+
+	aclb200_status aclb200_debug_seek(aclb200_context* context, const aclb200_clipset* clipset,
+		const aclb200_request* d_requests, uint32_t num_requests, const aclb200_options* options, aclb200_seek_state* d_out, void* stream)
+	{
+		DecodeParams params;
+		const aclb200_status status = make_params(context, clipset, d_requests, num_requests, options, d_out, true, true, params);
+		if (status != ACLB200_OK || num_requests == 0)
+			return status;
+		cudaSetDevice(context->device);
+		return finish_launch(context, launch_transform_debug_seek(params, d_out, static_cast<cudaStream_t>(stream)), "debug_seek");
+	}
+
+	aclb200_status aclb200_debug_unpack(aclb200_context* context, const aclb200_clipset* clipset,
+		const aclb200_request* d_requests, uint32_t num_requests, const aclb200_options* options, uint32_t which,
+		uint32_t max_animated_sub_tracks, uint32_t* d_out, void* stream)
+	{
+		DecodeParams params;
+		const aclb200_status status = make_params(context, clipset, d_requests, num_requests, options, d_out, true, true, params);
+		if (status != ACLB200_OK || num_requests == 0)
+			return status;
+		if (which > 1)
+			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "key frame selector must be 0 or 1");
+		params.debug_which = which;
+		params.debug_max_sub_tracks = max_animated_sub_tracks;
+		cudaSetDevice(context->device);
+		return finish_launch(context, launch_transform_debug_unpack(params, d_out, static_cast<cudaStream_t>(stream)), "debug_unpack");
+	}
+
+	uint64_t aclb200_launch_count(const aclb200_context* context)
+	{
+		return context != nullptr ? context->launch_count : 0;
+	}
+}

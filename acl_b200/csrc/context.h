@@ -1,0 +1,86 @@
+// acl_b200/csrc/context.h -- host-side objects behind the opaque handles of include/aclb200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/aclb200.h"
+#include "layout.h"
+
+struct aclb200_context
+{
+	int device = 0;
+	int num_sms = 0;
+	std::string last_error;
+	uint64_t launch_count = 0;
+
+	// scratch of the host-buffer convenience call
+	void* d_scratch_requests = nullptr;
+	size_t scratch_requests_bytes = 0;
+	void* d_scratch_out = nullptr;
+	size_t scratch_out_bytes = 0;
+	cudaStream_t host_stream = nullptr;
+};
+
+struct aclb200_clipset
+{
+	int device = 0;
+	aclb200_clipset_info info = {};
+	std::vector<aclb200::ClipDesc> host_clips;		// host mirror for the info queries and request validation
+	std::vector<uint32_t> host_looping;				// compressed_tracks::get_looping_policy() per clip
+	uint32_t max_animated_total = 0;
+
+	uint8_t* d_blobs = nullptr;
+	uint8_t* d_index = nullptr;
+	aclb200::ClipDesc* d_clips = nullptr;
+};
+
+namespace aclb200
+{
+	aclb200_status set_error(aclb200_context* context, aclb200_status status, const std::string& message);
+	aclb200_status check_cuda(aclb200_context* context, cudaError_t error, const char* what);
+
+	// One launch description shared by every kernel of the transform / scalar paths.
+	struct DecodeParams
+	{
+		const uint8_t* blobs;
+		const uint8_t* index;
+		const ClipDesc* clips;
+		const aclb200_request* requests;
+		const uint32_t* track_indices;		// decompress_track only
+		uint32_t num_requests;
+		uint32_t num_clips;
+		uint32_t max_tracks;
+		uint32_t requests_per_block;		// whole requests handled by one thread block
+		uint32_t max_tracks_magic;			// floor(2^32 / max_tracks) + 1, turns j / max_tracks into a mulhi
+		uint8_t* out;
+		uint64_t pose_stride;
+		uint32_t bone_stride;				// 48 or 40 (transform), components * 4 (scalar)
+
+		uint32_t rounding_policy;
+		uint32_t looping_policy;
+		uint32_t normalization;
+		uint32_t per_track_rounding;
+		uint32_t wrapping;
+		uint32_t clamp_sample_time;
+		uint32_t multiple_rotation_formats;
+		uint32_t default_mode[3];
+		float    constant_defaults[12];
+		const float* variable_defaults;
+		const uint8_t* per_track_policies;
+		uint32_t layout;
+		uint32_t debug_which;
+		uint32_t debug_max_sub_tracks;
+	};
+
+	// kernels.cu
+	cudaError_t launch_transform_decompress_tracks(const DecodeParams& params, uint32_t math_mode, cudaStream_t stream);
+	cudaError_t launch_transform_decompress_track(const DecodeParams& params, uint32_t math_mode, cudaStream_t stream);
+	cudaError_t launch_transform_debug_seek(const DecodeParams& params, aclb200_seek_state* d_out, cudaStream_t stream);
+	cudaError_t launch_transform_debug_unpack(const DecodeParams& params, uint32_t* d_out, cudaStream_t stream);
+	cudaError_t launch_scalar_decompress_tracks(const DecodeParams& params, cudaStream_t stream);
+	cudaError_t launch_scalar_decompress_track(const DecodeParams& params, cudaStream_t stream);
+}
