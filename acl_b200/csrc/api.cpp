@@ -332,6 +332,8 @@ extern "C"
 		error = cudaMemcpyAsync(context->d_scratch_requests, requests, needed_requests, cudaMemcpyHostToDevice, stream);
 		if (error == cudaSuccess && keeps_input)
 			error = cudaMemcpyAsync(context->d_scratch_out, out, needed_out, cudaMemcpyHostToDevice, stream);
+		else if (error == cudaSuccess)
+			error = cudaMemsetAsync(context->d_scratch_out, 0, needed_out, stream);	// rows no request writes (shorter clips, invalid requests) read as zero
 		if (error != cudaSuccess)
 			return check_cuda(context, error, "decompress_tracks_host: upload");
 

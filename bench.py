@@ -1,0 +1,459 @@
+#!/usr/bin/env python
+"""bench.py -- bone-poses/s of the batched seek + decompress_tracks hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--workload c2|c3|c5|c4] [--impl reference]
+
+One "step" = one pass of the hot path over the whole request batch of the workload:
+    c2 (default, BASELINE.json configs[1]): 10 000 clips x 100 bones x 60 samples, variable bit rate + range reduction,
+        600 000 requests = every clip x every (s + u) / 30 s, u ~ U[0, 1)  -> 60 M bone-poses per step per GPU
+    c3: 1 000 clips x 540 bones, 60 000 requests        c5: 125 000 clips x 30 bones x 32 samples per GPU, one random time per clip
+    c4: scalar float1f 4096 tracks x 1024 samples replicated x64, 65 536 requests (unit: track-samples/s)
+Inputs are SYNTHETIC clips compressed by the reference compressor (oracle/_ref, outside every timed region); when that
+library is absent the committed golden clip of the same shape is replicated at distinct addresses instead (config.clips says which).
+
+Default arm: the CUDA product through the C ABI (acl_b200). `value` = whole-job bone-poses/s with inputs resident in HBM,
+`e2e` = the same through aclb200_decompress_tracks_host with pinned HOST buffers (H2D of the requests + D2H of every pose inside
+the timed region). `--impl reference` times the reference's own CPU implementation (oracle/_ref: acl::decompression_context with the
+benchmark settings of tools/acl_decompressor/sources/benchmark.cpp:94-101) on all host threads for the same workload.
+Multi-GPU (torchrun, one rank per GPU): clips shard by rank with no data-path collective (weak scaling); NCCL carries only the
+barrier and the max-over-ranks of the device time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (kind, clips per GPU, bones, samples, description)
+    "c2": ("transform", 10000, 100, 60, "C2: 10k clips x 100 bones x 60 samples, variable bit rate + range reduction, 600k requests (every clip x every (s+u)/30)"),
+    "c3": ("transform", 1000, 540, 60, "C3: 1k clips x 540 bones x 60 samples, quatf_drop_w_variable + segmenting, 60k requests"),
+    "c5": ("transform", 125000, 30, 32, "C5: 125k clips per GPU x 30 bones x 32 samples, one random sample_time per clip"),
+    "c4": ("scalar", 64, 4096, 1024, "C4: scalar float1f 4096 tracks x 1024 samples replicated x64, 65536 requests"),
+}
+GOLDEN_FALLBACK = {"c2": "c2_100bones", "c3": "paragon_like", "c5": "c5_30x32", "c4": "float1_c4_small"}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# workload synthesis (never timed)
+# ------------------------------------------------------------------------------------------------------------------
+def make_workload(name: str, rank: int, clips_override: int | None):
+    kind, num_clips, bones, samples, description = WORKLOADS[name]
+    if clips_override:
+        num_clips = clips_override
+    from oracle import ref
+    distinct = ref.available()
+    if kind == "transform":
+        if distinct:
+            spec = ref.TransformSpec(num_tracks=bones, num_samples=samples, seed={"c2": 2000, "c3": 3000, "c5": 5000}[name] + rank * num_clips)
+            if name == "c3":
+                spec.scale_default_pct, spec.scale_constant_pct = 95, 0       # 5 % animated scale
+            t0 = time.time()
+            buffer, offsets, sizes = ref.compress_transform_batch(spec, num_clips)
+            log(f"[bench] rank {rank}: compressed {num_clips} clips with the reference in {time.time() - t0:.1f} s ({buffer.size / 1e6:.1f} MB)")
+        else:
+            buffer, offsets, sizes = replicate_golden(GOLDEN_FALLBACK[name], num_clips)
+        rng = np.random.default_rng({"c2": 7, "c3": 7, "c5": 11}[name] + rank)
+        if name == "c5":
+            req_clip = np.arange(num_clips, dtype=np.uint32)
+            req_time = (rng.random(num_clips) * ((samples - 1) / 30.0)).astype(np.float32)
+        else:
+            req_clip = np.repeat(np.arange(num_clips, dtype=np.uint32), samples)
+            s = np.tile(np.arange(samples, dtype=np.float64), num_clips)
+            req_time = ((s + rng.random(s.size)) / 30.0).astype(np.float32)
+        num_tracks = bones
+    else:
+        if distinct:
+            blob = ref.compress_scalar(ref.ScalarSpec(num_tracks=bones, num_samples=samples, seed=42, track_type=ref.TRACK_FLOAT1F, constant_pct=12, precision=0.001))
+            buffer, offsets, sizes = replicate_blob(blob, num_clips)
+        else:
+            buffer, offsets, sizes = replicate_golden(GOLDEN_FALLBACK[name], num_clips)
+            header = buffer[int(offsets[0]):int(offsets[0]) + 32].view(np.uint32)
+            bones, samples = int(header[4]), int(header[5])
+        rng = np.random.default_rng(42 + rank)
+        req_clip = np.repeat(np.arange(num_clips, dtype=np.uint32), samples)
+        s = np.tile(np.arange(samples, dtype=np.float64), num_clips)
+        req_time = ((s + rng.random(s.size)) / 30.0).astype(np.float32)
+        num_tracks = bones
+    return dict(kind=kind, name=name, description=description, buffer=buffer, offsets=offsets, sizes=sizes, req_clip=req_clip,
+                req_time=req_time, num_tracks=num_tracks, num_clips=num_clips, distinct=distinct and kind == "transform")
+
+
+def replicate_blob(blob: np.ndarray, copies: int):
+    stride = (blob.size + 63) & ~63
+    raw = np.zeros(stride * copies + 128, dtype=np.uint8)
+    shift = (-raw.ctypes.data) % 64
+    buffer = raw[shift:shift + stride * copies + 64]
+    for i in range(copies):
+        buffer[i * stride:i * stride + blob.size] = blob
+    return buffer, (np.arange(copies, dtype=np.uint64) * stride), np.full(copies, blob.size, dtype=np.uint32)
+
+
+def replicate_golden(golden_name: str, copies: int):
+    from tests import clips
+    return replicate_blob(clips.load_blob(golden_name), copies)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# algorithmic bytes of one launch (the reference's own decomp_touched_bytes, de-duplicated over the batch,
+# plus 40 B per bone-pose written)
+# ------------------------------------------------------------------------------------------------------------------
+def gather_u32(buffer: np.ndarray, byte_offsets: np.ndarray) -> np.ndarray:
+    idx = byte_offsets.astype(np.int64)[:, None] + np.arange(4, dtype=np.int64)[None, :]
+    return buffer[idx].copy().view(np.uint32)[:, 0]
+
+
+def algorithmic_bytes_transform(w) -> dict:
+    buffer, offsets = w["buffer"], w["offsets"].astype(np.int64)
+    req_clip, req_time = w["req_clip"].astype(np.int64), w["req_time"]
+    f = lambda rel: gather_u32(buffer, offsets + rel).astype(np.int64)
+    num_tracks, num_samples, misc = f(16), f(20), f(28)
+    rate = gather_u32(buffer, offsets + 24).view(np.float32).astype(np.float64)
+    nseg, nvar = f(32), f(36)
+    nar, nat, nas = f(40), f(44), f(48)
+    ncr, nct, ncs = f(52), f(56), f(60)
+    seg_headers = f(68)
+    has_scale = misc & 1
+    rot_fmt = (misc >> 4) & 15
+    trans_var, scale_var = (misc >> 3) & 1, (misc >> 2) & 1
+    stripped = (misc >> 10) & 1
+    hsize = np.where(stripped == 1, 20, 16)
+    entries = (num_tracks + 15) // 16
+    clip_bytes = 84 + np.where(nseg > 1, 4 * (nseg + 1), 0) + 4 * entries * np.where(has_scale == 1, 3, 2)
+    clip_bytes = clip_bytes + np.where(rot_fmt == 0, 16, 12) * ncr + 12 * (nct + np.where(has_scale == 1, ncs, 0))
+    clip_bytes = clip_bytes + np.where(rot_fmt == 3, 24 * nar, 0) + np.where(trans_var == 1, 24 * nat, 0) + np.where((has_scale == 1) & (scale_var == 1), 24 * nas, 0)
+    seg_meta = hsize + nvar + np.where(nseg > 1, 6 * nvar, 0)
+
+    # key frames touched by each request (clamp policy, no stripping: what the bench workloads contain)
+    t = np.clip(req_time.astype(np.float64), 0.0, None)
+    last = num_samples[req_clip] - 1
+    k0 = np.minimum(np.floor(t * rate[req_clip]).astype(np.int64), last)
+    k1 = np.minimum(k0 + 1, last)
+    max_samples = int(num_samples.max()) + 1
+    keys = np.unique(np.concatenate([req_clip * max_samples + k0, req_clip * max_samples + k1]))
+    key_clip, key_frame = keys // max_samples, keys % max_samples
+
+    # segment of each touched key frame and its pose size
+    max_seg = int(nseg.max())
+    starts = np.zeros((len(offsets), max_seg + 1), dtype=np.int64)
+    pose_bits = np.zeros((len(offsets), max_seg), dtype=np.int64)
+    for s in range(max_seg):
+        valid = nseg > s
+        pose_bits[valid, s] = gather_u32(buffer, offsets[valid] + 32 + seg_headers[valid] + s * hsize[valid])
+        multi = valid & (nseg > 1)
+        starts[multi, s] = gather_u32(buffer, offsets[multi] + 84 + 4 * s)
+    starts[np.arange(len(offsets)), nseg] = np.iinfo(np.int64).max // 2
+    for s in range(max_seg + 1):
+        starts[nseg < s, s] = np.iinfo(np.int64).max // 2
+    key_seg = (starts[key_clip] <= key_frame[:, None]).sum(axis=1) - 1
+    key_seg = np.clip(key_seg, 0, None)
+    key_bytes = (pose_bits[key_clip, key_seg] + 7) // 8
+    touched_clips = np.unique(req_clip)
+    touched_segments = np.unique(key_clip * (max_seg + 1) + key_seg)
+
+    in_bytes = int(clip_bytes[touched_clips].sum() + seg_meta[touched_segments // (max_seg + 1)].sum() + key_bytes.sum())
+    out_bytes = int((num_tracks[req_clip] * 40).sum())
+    return dict(in_bytes=in_bytes, out_bytes=out_bytes, total=in_bytes + out_bytes, units=int(num_tracks[req_clip].sum()))
+
+
+def algorithmic_bytes_scalar(w) -> dict:
+    from tests import clips  # noqa: F401  (only for the lane constants elsewhere)
+    buffer, offsets = w["buffer"], w["offsets"].astype(np.int64)
+    req_clip, req_time = w["req_clip"].astype(np.int64), w["req_time"]
+    o = int(offsets[0])
+    hdr = buffer[o:o + 52].view(np.uint32)
+    track_type, num_tracks, num_samples = int(buffer[o + 15]), int(hdr[4]), int(hdr[5])
+    bits_per_frame, metadata = int(hdr[8]), int(hdr[9])
+    comps = track_type + 1 if track_type <= 3 else 4
+    rates = buffer[o + 32 + metadata:o + 32 + metadata + num_tracks]
+    table = np.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 32])
+    bits = table[rates]
+    per_clip = 52 + num_tracks + 4 * comps * int((bits == 0).sum()) + 8 * comps * int(((bits != 0) & (bits != 32)).sum())
+    k0 = np.minimum(np.floor(np.clip(req_time.astype(np.float64), 0, None) * 30.0).astype(np.int64), num_samples - 1)
+    k1 = np.minimum(k0 + 1, num_samples - 1)
+    keys = np.unique(np.concatenate([req_clip * (num_samples + 1) + k0, req_clip * (num_samples + 1) + k1]))
+    in_bytes = per_clip * len(np.unique(req_clip)) + len(keys) * ((bits_per_frame + 7) // 8)
+    out_bytes = len(req_clip) * num_tracks * comps * 4
+    return dict(in_bytes=int(in_bytes), out_bytes=int(out_bytes), total=int(in_bytes + out_bytes), units=len(req_clip) * num_tracks)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks under load
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device_index: int):
+        self.device_index = device_index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "20",
+                                          "-i", str(self.device_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, sm_max, reasons = [], [], set()
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); sm_max.append(float(parts[2]))
+            except ValueError:
+                continue
+            for label, value in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if value.lower().startswith("active"):
+                    reasons.add(label)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(sm_max)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline (oracle/_ref on the host cores)
+# ------------------------------------------------------------------------------------------------------------------
+def host_blobs(w):
+    return [w["buffer"][int(o):int(o) + int(s)] for o, s in zip(w["offsets"], w["sizes"])]
+
+
+def cpu_reference_pass(w, blobs, sample_requests: int, threads: int, repeats: int):
+    """Seconds for ONE pass of the reference CPU decoder over the first `sample_requests` requests (fastest of `repeats`)."""
+    from oracle import ref
+    return ref.bench(blobs, w["req_clip"][:sample_requests], w["req_time"][:sample_requests], w["num_tracks"], threads, repeats,
+                     scalar=(w["kind"] == "scalar"))
+
+
+def bounded_sample(w, threads: int, seconds: float = 4.0) -> int:
+    # ~45 M bone-poses/s/core (BASELINE.md probe) -> keep one pass around `seconds`
+    per_request = max(w["num_tracks"], 1)
+    budget = int(seconds * 45e6 * max(threads, 1) / per_request)
+    return int(min(len(w["req_clip"]), max(budget, 1000)))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--clips", type=int, default=None, help="override the number of clips per GPU (debugging)")
+    ap.add_argument("--layout", default="qvv40", choices=["qvv40", "qvv48"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    unit = "bone-poses/s" if WORKLOADS[args.workload][0] == "transform" else "track-samples/s"
+    metric = "bone_poses_per_sec" if unit == "bone-poses/s" else "track_samples_per_sec"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import ref
+        w = make_workload(args.workload, 0, args.clips)
+        blobs = host_blobs(w)
+        threads = ref.lib().aclref_hardware_threads() if ref.available() else 1
+        sample = bounded_sample(w, threads)
+        for _ in range(args.warmup):
+            cpu_reference_pass(w, blobs, sample, threads, 1)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_reference_pass(w, blobs, sample, threads, 1)
+        elapsed = time.perf_counter() - t0
+        units = sample * w["num_tracks"]
+        value = units * args.steps / elapsed
+        print(json.dumps({
+            "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": w["description"], "clips": "distinct" if w["distinct"] else "replicated"},
+            "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "reference",
+                             "sample": f"{sample} of {len(w['req_clip'])} requests per step, acl::decompression_context<benchmark settings> on {threads} host threads"},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    import torch
+    import acl_b200 as ab
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    distributed = world > 1
+    if distributed:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    w = make_workload(args.workload, rank, args.clips)
+    is_transform = w["kind"] == "transform"
+    ctx = ab.Context(local_rank)
+    clipset = ctx.upload_packed(w["buffer"], w["offsets"], w["sizes"])
+    requests = ab.make_requests(w["req_clip"], w["req_time"])
+    num_requests = len(requests)
+    layout = ab.LAYOUT_QVV40 if args.layout == "qvv40" else ab.LAYOUT_QVV48
+    options = ab.Options(output_layout=layout)
+    bone_bytes = (40 if layout == ab.LAYOUT_QVV40 else 48) if is_transform else 4 * clipset.components
+    pose_bytes = clipset.max_tracks * bone_bytes
+    d_requests = torch.from_numpy(requests.view(np.uint8)).cuda()
+    d_out = torch.empty(num_requests * pose_bytes, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def launch():
+        if is_transform:
+            ctx.decompress_tracks(clipset, d_requests, num_requests, options, d_out, stream)
+        else:
+            ctx.scalar_decompress_tracks(clipset, d_requests, num_requests, options, d_out, stream)
+
+    alg = algorithmic_bytes_transform(w) if is_transform else algorithmic_bytes_scalar(w)
+    units_per_step = alg["units"]
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        launch()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches_before = ctx.launch_count
+    start = torch.cuda.Event(enable_timing=True)
+    stop = torch.cuda.Event(enable_timing=True)
+    per_launch = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    start.record(stream)
+    for a, b in per_launch:
+        a.record(stream)
+        launch()
+        b.record(stream)
+    stop.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    gpu_launches = ctx.launch_count - launches_before
+    elapsed_ms = start.elapsed_time(stop)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in per_launch]))
+    if distributed:
+        t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = units_per_step * world * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- e2e: host buffers through aclb200_decompress_tracks_host ----
+    e2e = None
+    if not args.no_e2e:
+        h_requests = torch.from_numpy(requests.view(np.uint8).copy()).pin_memory()
+        h_out = torch.empty(num_requests * pose_bytes, dtype=torch.uint8).pin_memory()
+        req_np = h_requests.numpy().view(ab.api.REQUEST_DTYPE)
+        out_np = h_out.numpy()
+        e2e_steps = max(2, min(args.steps, 5))
+        ctx.decompress_tracks_host(clipset, req_np, options, out_np)     # warm-up (allocates the device scratch)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.decompress_tracks_host(clipset, req_np, options, out_np)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if distributed:
+            t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e = {"value": units_per_step * world * e2e_steps / e2e_s, "unit": unit, "h2d_bytes_per_step": int(requests.nbytes),
+               "d2h_bytes_per_step": int(num_requests * pose_bytes), "steps": e2e_steps}
+        del h_out
+
+    if rank != 0:
+        if distributed:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant (only) kernel ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    written_per_step = alg["out_bytes"] * bone_bytes // 40 if is_transform else alg["out_bytes"]
+    achieved = (alg["in_bytes"] + alg["out_bytes"]) / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    traffic_path = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
+    if os.path.exists(traffic_path):
+        traffic = json.load(open(traffic_path)).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "transform_decompress_tracks_kernel" if is_transform else "scalar_decompress_tracks_kernel",
+                "kernel_ms": kernel_ms, "algorithmic_bytes_in": alg["in_bytes"], "algorithmic_bytes_out": alg["out_bytes"],
+                "bytes_written": int(written_per_step), "peak_source": peak_src}
+
+    # ---- CPU baseline (reported, not the target) ----
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import ref
+        if ref.available():
+            blobs = host_blobs(w)
+            threads = int(ref.lib().aclref_hardware_threads())
+            sample = bounded_sample(w, threads)
+            seconds = cpu_reference_pass(w, blobs, sample, threads, 3)
+            cpu_baseline = {"value": sample * w["num_tracks"] / seconds, "unit": unit, "cores": threads, "kind": "reference",
+                            "sample": f"{sample} of {num_requests} requests, fastest of 3 passes, acl::decompression_context<benchmark settings> on {threads} host threads"}
+        else:
+            from oracle import port
+            blobs = host_blobs(w)
+            sample = min(num_requests, 20000)
+            seconds = port.bench_transform(blobs, w["req_clip"][:sample], w["req_time"][:sample], w["num_tracks"])
+            cpu_baseline = {"value": sample * w["num_tracks"] / seconds, "unit": unit, "cores": 1, "kind": "port",
+                            "sample": f"{sample} of {num_requests} requests, plain-C port, 1 thread"}
+
+    result = {
+        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": w["description"], "clips": "distinct" if w["distinct"] else "replicated", "clips_per_gpu": w["num_clips"],
+                   "requests_per_step_per_gpu": num_requests, "bones": w["num_tracks"], "layout": args.layout,
+                   "l2": f"inputs larger than L2: {clipset.blob_bytes / 1e6:.0f} MB compressed + {num_requests * pose_bytes / 1e6:.0f} MB of poses per step vs 126 MB L2",
+                   "math": "exact (bit-identical to the reference)", "parallelism": f"clip-sharded x{world}, no data-path collective"},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
+    }
+    print(json.dumps(result))
+    if distributed:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
