@@ -9,7 +9,6 @@ namespace aclb200
 {
 	aclb200_status build_clipset(aclb200_context* context, const std::function<const uint8_t*(uint32_t)>& get_blob, const uint32_t* sizes,
 		uint32_t num_clips, bool check_hash, aclb200_clipset** out_clipset, uint32_t* out_failed_clip);
-	void plan_launch(DecodeParams& params);
 
 	namespace
 	{
@@ -42,13 +41,14 @@ namespace aclb200
 				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "per track rounding must be enabled to seek with the per_track policy");
 
 			std::memset(&params, 0, sizeof(params));
-			params.blobs = clipset->d_blobs;
-			params.index = clipset->d_index;
+			params.data = clipset->d_data;
 			params.clips = clipset->d_clips;
 			params.requests = d_requests;
 			params.num_requests = num_requests;
 			params.num_clips = clipset->info.num_clips;
 			params.max_tracks = clipset->info.max_tracks;
+			for (int k = 0; k < 3; ++k)
+				params.max_animated[k] = clipset->max_animated[k];
 			params.out = static_cast<uint8_t*>(d_out);
 			if (is_transform)
 				params.bone_stride = options->output_layout == ACLB200_LAYOUT_QVV48 ? 48u : 40u;
@@ -73,7 +73,7 @@ namespace aclb200
 			params.variable_defaults = options->d_variable_defaults;
 			params.per_track_policies = options->d_per_track_rounding;
 			params.layout = options->output_layout;
-			plan_launch(params);
+			plan_launch(params, is_transform && !single_track ? clipset->max_key_frame_bytes : 0u, context->max_dynamic_smem);
 			return ACLB200_OK;
 		}
 
@@ -151,7 +151,8 @@ extern "C"
 			return ACLB200_ERR_OUT_OF_MEMORY;
 		context->device = device;
 		context->num_sms = prop.multiProcessorCount;
-		if (prop.major < 10)
+		context->max_dynamic_smem = int(prop.sharedMemPerBlockOptin);
+		if (prop.major < 10 || cudaSetDevice(device) != cudaSuccess || configure_kernels(context->max_dynamic_smem) != cudaSuccess)
 		{
 			// the kernels are compiled for sm_100a only
 			delete context;
@@ -202,8 +203,7 @@ extern "C"
 		if (clipset == nullptr)
 			return;
 		cudaSetDevice(clipset->device);
-		cudaFree(clipset->d_blobs);
-		cudaFree(clipset->d_index);
+		cudaFree(clipset->d_data);
 		cudaFree(clipset->d_clips);
 		delete clipset;
 		(void)context;

@@ -1,14 +1,16 @@
-// acl_b200/csrc/clipset.cpp -- host side of aclb200_upload_clips: validate the caller's compressed_tracks blobs,
-// lay them out for HBM and build the acceleration index (see layout.h).
+// acl_b200/csrc/clipset.cpp -- host side of aclb200_upload_clips: validate the caller's compressed_tracks blobs and
+// transcode each one into the GPU-native clip image described in layout.h.
 //
 // This is the batched counterpart of decompression_context::initialize()
 // (includes/acl/decompression/impl/decompress.impl.h:66-83 -> initialize_v0,
-// includes/acl/decompression/impl/decompression.transform.h:84-132 / decompression.scalar.h:99-123): the
-// reference caches a handful of header fields per context; we resolve every offset the decoder needs once per
-// clip and, because a GPU thread cannot run the reference's serial cursors, also tabulate the per sub-track bit
-// offsets of every segment.
+// includes/acl/decompression/impl/decompression.transform.h:84-132 / decompression.scalar.h:99-123). The reference
+// caches a handful of header fields per context and re-derives everything else on every seek with serial cursors; a
+// GPU thread cannot run those cursors, so the offsets, ranks and per sub-track bit positions are tabulated here once.
+// Float values computed here (W of constant rotations, 1/(2^n - 1)) use the same IEEE-754 single precision operations
+// in the same order as the reference's decoder, so nothing about the results changes.
 #include "context.h"
 
+#include <cmath>
 #include <cstring>
 #include <functional>
 #include <limits>
@@ -44,17 +46,50 @@ namespace aclb200
 			return float(num_samples - 1) / sample_rate;
 		}
 
+		// PackedTableEntry::max_value, math/vector4_packing.h:927-929: a float division evaluated in float
+		float inv_max_value(uint32_t num_bits)
+		{
+			return 1.0F / float((1u << num_bits) - 1u);
+		}
+
+		// Growable clip image with 16 byte aligned sections
+		struct image_builder
+		{
+			std::vector<uint8_t>& bytes;
+			size_t base;
+			explicit image_builder(std::vector<uint8_t>& bytes_) : bytes(bytes_), base(bytes_.size()) {}
+			uint32_t reserve(size_t size)
+			{
+				const size_t offset = align_up64(bytes.size() - base, k_section_alignment);
+				bytes.resize(base + offset + size, 0);
+				return uint32_t(offset);
+			}
+			uint8_t* at(uint32_t offset) { return bytes.data() + base + offset; }
+		};
+
+		// Copies `num_bytes` of a big-endian bit stream as byte-swapped 32-bit words (so word i holds stream bits [32 i, 32 i + 32)
+		// with bit 0 of the stream in the MSB) and leaves k_stream_tail zero bytes behind it.
+		uint32_t append_stream(image_builder& image, const uint8_t* src, size_t num_bytes)
+		{
+			const size_t padded = align_up64(num_bytes, 4);
+			const uint32_t offset = image.reserve(padded + k_stream_tail);
+			uint8_t* dst = image.at(offset);
+			for (size_t i = 0; i < num_bytes; ++i)
+				dst[(i & ~size_t(3)) + (3 - (i & 3))] = src[i];
+			return offset;
+		}
+
 		struct parse_result
 		{
 			ClipDesc desc;
-			std::vector<uint8_t> index;		// this clip's index block
 			uint32_t looping_policy;
 			uint32_t track_type;
+			uint32_t max_key_frame_bytes;
 		};
 
-		// Returns an empty string on success, else why the clip is rejected. `unsupported` tells apart valid ACL data we
-		// refuse (database clips) from invalid buffers.
-		std::string parse_clip(const uint8_t* blob, uint32_t size, bool check_hash, parse_result& out, bool& unsupported)
+		// Validates one blob and appends its clip image to `data`. Returns an empty string on success, else why the clip is
+		// rejected; `unsupported` tells apart valid ACL data we refuse (database clips) from invalid buffers.
+		std::string transcode_clip(const uint8_t* blob, uint32_t size, bool check_hash, std::vector<uint8_t>& data, parse_result& out, bool& unsupported)
 		{
 			unsupported = false;
 
@@ -100,9 +135,11 @@ namespace aclb200
 			d.size = stored_size;
 			out.looping_policy = is_wrap ? ACLB200_LOOP_WRAP : ACLB200_LOOP_CLAMP;
 			out.track_type = track_type;
+			out.max_key_frame_bytes = 0;
 			if (is_wrap)
 				d.flags |= k_clip_wrap;
 
+			image_builder image(data);
 			const uint8_t* th = blob + k_type_header_offset;
 			auto in_bounds = [&](uint64_t offset_from_blob, uint64_t bytes) { return offset_from_blob + bytes <= stored_size; };
 
@@ -121,8 +158,7 @@ namespace aclb200
 				const uint8_t* table = version == k_version_first ? k_bit_rate_num_bits_v0 : k_bit_rate_num_bits;
 				const uint32_t table_size = version == k_version_first ? sizeof(k_bit_rate_num_bits_v0) : sizeof(k_bit_rate_num_bits);
 
-				out.index.resize(size_t(num_tracks) * sizeof(ScalarTrackDesc));
-				ScalarTrackDesc* tracks = reinterpret_cast<ScalarTrackDesc*>(out.index.data());
+				d.bone_table_offset = image.reserve(size_t(num_tracks) * sizeof(ScalarTrackDesc));
 				uint32_t bit_offset = 0, constant_index = 0, range_index = 0;
 				for (uint32_t track = 0; track < num_tracks; ++track)
 				{
@@ -130,37 +166,43 @@ namespace aclb200
 					if (bit_rate >= table_size)
 						return "invalid scalar bit rate";
 					const uint32_t num_bits = table[bit_rate];
-					tracks[track].bit_offset = bit_offset;
+					ScalarTrackDesc desc = {};
+					desc.bit_offset = bit_offset;
+					desc.inv_max = 1.0F;
 					if (num_bits == 0)
 					{
-						tracks[track].value_index_and_bits = (constant_index << 8) | 0u;
+						desc.value_index_and_bits = (constant_index << 8) | 0u;
 						constant_index += num_components;
 					}
 					else if (num_bits == 32)
-						tracks[track].value_index_and_bits = 32u;
+						desc.value_index_and_bits = 32u;
 					else
 					{
-						tracks[track].value_index_and_bits = (range_index << 8) | num_bits;
+						desc.value_index_and_bits = (range_index << 8) | num_bits;
+						desc.inv_max = inv_max_value(num_bits);
 						range_index += num_components * 2;
 					}
+					std::memcpy(image.at(d.bone_table_offset) + size_t(track) * sizeof(ScalarTrackDesc), &desc, sizeof(desc));
 					bit_offset += num_bits * num_components;
 				}
 				if (bit_offset != num_bits_per_frame)
 					return "scalar bit rates do not add up to num_bits_per_frame";
 				if (!in_bounds(constant_offset, uint64_t(constant_index) * 4) || !in_bounds(range_offset, uint64_t(range_index) * 4))
 					return "scalar constant / range values out of bounds";
-				if (num_samples != 0 && !in_bounds(animated_offset, (uint64_t(num_bits_per_frame) * num_samples + 7) / 8))
+				const uint64_t stream_bytes = (uint64_t(num_bits_per_frame) * num_samples + 7) / 8;
+				if (num_samples != 0 && !in_bounds(animated_offset, stream_bytes))
 					return "scalar animated values out of bounds";
-				if ((constant_offset & 3) != 0 || (range_offset & 3) != 0)
-					return "scalar constant / range values are not 4 byte aligned";
+
+				d.const_rot_offset = image.reserve(size_t(constant_index) * 4 + 16);
+				std::memcpy(image.at(d.const_rot_offset), blob + constant_offset, size_t(constant_index) * 4);
+				d.const_vec_offset = image.reserve(size_t(range_index) * 4 + 16);
+				std::memcpy(image.at(d.const_vec_offset), blob + range_offset, size_t(range_index) * 4);
+				d.seg_table_offset = append_stream(image, blob + animated_offset, size_t(stream_bytes));
 
 				d.num_segments = 1;
 				d.samples_per_segment = num_samples;
-				d.num_constant[0] = num_bits_per_frame;
-				d.constant_offset[0] = constant_offset;
-				d.constant_offset[1] = range_offset;
-				d.constant_offset[2] = animated_offset;
-				d.bone_table_offset = 0;
+				d.num_animated_total = num_bits_per_frame;
+				d.image_size = image.reserve(0);
 				return std::string();
 			}
 
@@ -194,6 +236,7 @@ namespace aclb200
 			if (num_tracks == 0)
 			{
 				d.num_segments = 0;
+				d.image_size = image.reserve(0);
 				return std::string();	// empty track list: seek/decompress are no-ops (decompression.transform.h:211-212)
 			}
 			if (num_segments == 0)
@@ -204,26 +247,26 @@ namespace aclb200
 
 			const bool rot_variable = rotation_format == k_rot_drop_w_variable;
 			const bool rot_full = rotation_format == k_rot_full;
-			const bool trans_variable = translation_format == 1;
-			const bool scale_variable = scale_format == 1;
+			const bool variable[3] = { rot_variable, translation_format == 1, has_scale && scale_format == 1 };
 			const uint32_t raw_marker = version >= k_version_raw31 ? 31u : 32u;		// animated_track_cache.transform.h:523
 			const uint32_t segment_header_size = has_stripped ? 20u : 16u;				// compressed_headers.h:171-197
 			const uint32_t num_entries = (num_tracks + 15) / 16;
 			const uint32_t padded_rotations = align_up(num_animated[0], 4);
 			const uint32_t num_animated_total = num_animated[0] + num_animated[1] + num_animated[2];
+			const uint32_t num_kinds = has_scale ? 3u : 2u;
 
 			if (!in_bounds(segment_headers_offset, uint64_t(segment_header_size) * num_segments))
 				return "segment headers out of bounds";
-			if (!in_bounds(sub_track_types_offset, uint64_t(num_entries) * 4 * (has_scale ? 3 : 2)))
+			if (!in_bounds(sub_track_types_offset, uint64_t(num_entries) * 4 * num_kinds))
 				return "sub-track types out of bounds";
 			if (num_segments > 1 && !in_bounds(84, uint64_t(num_segments + 1) * 4))
 				return "segment start indices out of bounds";
 
 			d.flags |= has_scale ? k_clip_has_scale : 0u;
 			d.flags |= ((misc >> 1) & 1) ? k_clip_default_scale_one : 0u;
-			d.flags |= rot_variable ? k_clip_rot_variable : 0u;
-			d.flags |= trans_variable ? k_clip_trans_variable : 0u;
-			d.flags |= (has_scale && scale_variable) ? k_clip_scale_variable : 0u;
+			d.flags |= variable[0] ? k_clip_rot_variable : 0u;
+			d.flags |= variable[1] ? k_clip_trans_variable : 0u;
+			d.flags |= variable[2] ? k_clip_scale_variable : 0u;
 			d.flags |= rot_full ? k_clip_rot_full : 0u;
 			d.flags |= has_stripped ? k_clip_stripped : 0u;
 			d.flags |= num_segments > 1 ? k_clip_has_segments : 0u;
@@ -235,45 +278,26 @@ namespace aclb200
 				d.num_constant[k] = num_constant[k];
 			}
 			d.num_animated_total = num_animated_total;
-			d.start_indices_offset = 84;		// transform_tracks_header::get_segment_start_indices, compressed_headers.h:271-272
 
 			// constant_track_cache_v0::initialize, constant_track_cache.transform.h:96-110
-			d.constant_offset[0] = constant_data_offset;
-			d.constant_offset[1] = d.constant_offset[0] + (rot_full ? 16u : 12u) * num_constant[0];
-			d.constant_offset[2] = d.constant_offset[1] + 12u * num_constant[1];
-			if (!in_bounds(d.constant_offset[2], 12ull * num_constant[2]))
+			const uint32_t constant_offset[3] = { constant_data_offset, constant_data_offset + (rot_full ? 16u : 12u) * num_constant[0],
+				constant_data_offset + (rot_full ? 16u : 12u) * num_constant[0] + 12u * num_constant[1] };
+			if (!in_bounds(constant_offset[2], 12ull * num_constant[2]))
 				return "constant track data out of bounds";
 
 			// animated_track_cache_v0::initialize, animated_track_cache.transform.h:1259-1262,1293-1294
-			d.clip_range_offset[0] = clip_range_data_offset;
-			d.clip_range_offset[1] = d.clip_range_offset[0] + (rot_variable ? 24u * num_animated[0] : 0u);
-			d.clip_range_offset[2] = d.clip_range_offset[1] + (trans_variable ? 24u * num_animated[1] : 0u);
+			const uint32_t clip_range_offset[3] = { clip_range_data_offset, clip_range_data_offset + (variable[0] ? 24u * num_animated[0] : 0u),
+				clip_range_data_offset + (variable[0] ? 24u * num_animated[0] : 0u) + (variable[1] ? 24u * num_animated[1] : 0u) };
+			if ((variable[0] || variable[1] || variable[2]) && !in_bounds(clip_range_offset[2], variable[2] ? 24ull * num_animated[2] : 0ull))
+				return "clip range data out of bounds";
+
+			// ---- BoneDesc + the bone each animated sub-track belongs to ----
+			d.bone_table_offset = image.reserve(size_t(num_tracks) * 8);
+			std::vector<uint32_t> animated_bone[3];
 			{
-				const uint64_t clip_range_end = uint64_t(d.clip_range_offset[2]) + ((has_scale && scale_variable) ? 24ull * num_animated[2] : 0ull);
-				if ((rot_variable || trans_variable || (has_scale && scale_variable)) && clip_range_end > stored_size)
-					return "clip range data out of bounds";
-			}
-
-			// Sections the kernels read as aligned words; the reference writer guarantees this
-			// (compression/impl/compress.transform.impl.h:316-327), anything else is not an ACL buffer.
-			if ((d.constant_offset[0] & 3) != 0 || (d.clip_range_offset[0] & 3) != 0)
-				return "constant / clip range data is not 4 byte aligned";
-
-			// ---- index block: BoneDesc[num_tracks] | SegDesc[num_segments] | entries[num_segments][num_animated_total] ----
-			const size_t bone_table_bytes = align_up64(uint64_t(num_tracks) * 8, 16);
-			const size_t seg_table_bytes = size_t(num_segments) * sizeof(SegDesc);
-			const size_t entries_bytes_per_segment = align_up64(uint64_t(num_animated_total) * 4, 16);
-			out.index.assign(bone_table_bytes + seg_table_bytes + entries_bytes_per_segment * num_segments, 0);
-			d.bone_table_offset = 0;
-			d.seg_table_offset = uint32_t(bone_table_bytes);
-
-			// Bone table: rank of each bone among the constant / animated sub-tracks of its kind, i.e. the prefix popcounts of
-			// decompress_track_v0 (decompression.transform.h:1873-1891) evaluated once for every bone.
-			{
-				uint64_t* bones = reinterpret_cast<uint64_t*>(out.index.data());
 				uint32_t constant_rank[3] = { 0, 0, 0 };
-				uint32_t animated_rank[3] = { 0, 0, 0 };
-				const uint32_t num_kinds = has_scale ? 3u : 2u;
+				for (uint32_t kind = 0; kind < num_kinds; ++kind)
+					animated_bone[kind].reserve(num_animated[kind]);
 				for (uint32_t track = 0; track < num_tracks; ++track)
 				{
 					uint64_t desc = 0;
@@ -288,18 +312,119 @@ namespace aclb200
 						if (type == 1)
 							rank = constant_rank[kind]++;
 						else if (type == 2)
-							rank = animated_rank[kind]++;
+						{
+							rank = uint32_t(animated_bone[kind].size());
+							animated_bone[kind].push_back(track);
+						}
 						desc |= (uint64_t(type) | (uint64_t(rank) << 2)) << (k_bone_kind_shift * kind);
 					}
-					bones[track] = desc;
+					std::memcpy(image.at(d.bone_table_offset) + size_t(track) * 8, &desc, 8);
 				}
 				for (uint32_t kind = 0; kind < num_kinds; ++kind)
-					if (constant_rank[kind] != num_constant[kind] || animated_rank[kind] != num_animated[kind])
+					if (constant_rank[kind] != num_constant[kind] || animated_bone[kind].size() != num_animated[kind])
 						return "sub-track types disagree with the header counts";
 			}
 
-			// Segment tables
-			SegDesc* segs = reinterpret_cast<SegDesc*>(out.index.data() + bone_table_bytes);
+			// ---- constant rotations: W reconstruction (and normalisation) done once, with the decoder's own operations ----
+			d.const_rot_offset = image.reserve(size_t(num_constant[0]) * 32);
+			for (uint32_t index = 0; index < num_constant[0]; ++index)
+			{
+				float q[4];
+				if (rot_full)
+				{
+					for (int c = 0; c < 4; ++c)
+						q[c] = rd_f32(blob + constant_offset[0] + index * 16 + c * 4);
+				}
+				else
+				{
+					// SOA groups of 4 with an unpadded last group (constant_track_cache.transform.h:153-170)
+					const uint32_t group = index / 4, lane = index % 4;
+					const uint32_t remaining = num_constant[0] - group * 4;
+					const uint32_t group_size = remaining < 4 ? remaining : 4;
+					const uint8_t* p = blob + constant_offset[0] + group * 48 + lane * 4;
+					q[0] = rd_f32(p + group_size * 4 * 0);
+					q[1] = rd_f32(p + group_size * 4 * 1);
+					q[2] = rd_f32(p + group_size * 4 * 2);
+					// quat_from_positive_w4, math/quatf.h:135-147
+					float r = 1.0F - q[0] * q[0];
+					r = r - q[1] * q[1];
+					r = r - q[2] * q[2];
+					q[3] = std::sqrt(std::fabs(r));
+				}
+				float n[4] = { q[0], q[1], q[2], q[3] };
+				if (!rot_full)
+				{
+					// quat_normalize4, math/quatf.h:200-211 (policy `always`, constant_track_cache.transform.h:172-175)
+					float dot = n[0] * n[0];
+					dot = n[1] * n[1] + dot;
+					dot = n[2] * n[2] + dot;
+					dot = n[3] * n[3] + dot;
+					const float inv_len = 1.0F / std::sqrt(dot);
+					for (int c = 0; c < 4; ++c)
+						n[c] = n[c] * inv_len;
+				}
+				std::memcpy(image.at(d.const_rot_offset) + size_t(index) * 32, q, 16);
+				std::memcpy(image.at(d.const_rot_offset) + size_t(index) * 32 + 16, n, 16);
+			}
+
+			// ---- constant translations then scales, one float4 each ----
+			d.const_vec_offset = image.reserve(size_t(num_constant[1] + num_constant[2]) * 16);
+			for (uint32_t kind = 1; kind <= 2; ++kind)
+				for (uint32_t index = 0; index < num_constant[kind]; ++index)
+				{
+					const size_t slot = (kind == 2 ? num_constant[1] : 0u) + index;
+					std::memcpy(image.at(d.const_vec_offset) + slot * 16, blob + constant_offset[kind] + index * 12, 12);
+				}
+
+			// ---- AnimDesc: clip range + destination bone of every animated sub-track ----
+			d.anim_table_offset = image.reserve(size_t(num_animated_total) * sizeof(AnimDesc));
+			{
+				uint32_t slot = 0;
+				for (uint32_t kind = 0; kind < 3; ++kind)
+					for (uint32_t index = 0; index < num_animated[kind]; ++index, ++slot)
+					{
+						AnimDesc anim = {};
+						anim.bone = animated_bone[kind][index];
+						anim.extent[0] = anim.extent[1] = anim.extent[2] = 1.0F;
+						if (variable[kind])
+						{
+							if (kind == 0)
+							{
+								// remap_clip_range_data4, animated_track_cache.transform.h:391-418: SOA per group of 4, last group unpadded
+								const uint32_t group = index / 4, lane = index % 4;
+								const uint32_t remaining = num_animated[0] - group * 4;
+								const uint32_t group_size = remaining < 4 ? remaining : 4;
+								const uint8_t* p = blob + clip_range_offset[0] + group * 96 + lane * 4;
+								for (int c = 0; c < 3; ++c)
+								{
+									anim.min[c] = rd_f32(p + group_size * 4 * c);
+									anim.extent[c] = rd_f32(p + group_size * 4 * (3 + c));
+								}
+							}
+							else
+							{
+								// unpack_animated_vector3, :949-958: min xyz then extent xyz
+								const uint8_t* p = blob + clip_range_offset[kind] + index * 24;
+								for (int c = 0; c < 3; ++c)
+								{
+									anim.min[c] = rd_f32(p + 4 * c);
+									anim.extent[c] = rd_f32(p + 12 + 4 * c);
+								}
+							}
+						}
+						std::memcpy(image.at(d.anim_table_offset) + size_t(slot) * sizeof(AnimDesc), &anim, sizeof(anim));
+					}
+			}
+
+			// ---- segment start indices (+ sentinel), transform_tracks_header::get_segment_start_indices, compressed_headers.h:271-272 ----
+			if (num_segments > 1)
+			{
+				d.start_indices_offset = image.reserve(size_t(num_segments + 1) * 4);
+				std::memcpy(image.at(d.start_indices_offset), blob + 84, size_t(num_segments + 1) * 4);
+			}
+
+			// ---- per segment: SegDesc, entries, stream ----
+			d.seg_table_offset = image.reserve(size_t(num_segments) * sizeof(SegDesc));
 			for (uint32_t segment = 0; segment < num_segments; ++segment)
 			{
 				const uint8_t* header = blob + segment_headers_offset + segment_header_size * segment;
@@ -317,18 +442,14 @@ namespace aclb200
 				if (!in_bounds(format_offset, num_variable) || !in_bounds(range_offset, range_size) || !in_bounds(animated_offset, 0))
 					return "segment data out of bounds";
 
-				SegDesc& seg = segs[segment];
-				seg.animated_offset = animated_offset;
+				SegDesc seg = {};
 				seg.pose_bit_size = pose_bit_size;
 				seg.sample_indices = has_stripped ? rd_u32(header + 16) : 0xFFFFFFFFu;
-				seg.entries_offset = uint32_t(bone_table_bytes + seg_table_bytes + entries_bytes_per_segment * segment);
-				seg.format_offset = format_offset;
-				// rotation range data is padded to groups of 4, translations / scales are not (animated_track_cache.transform.h:1271-1276,1300-1302)
-				seg.range_offset[0] = range_offset;
-				seg.range_offset[1] = seg.range_offset[0] + (rot_variable ? 6u * padded_rotations : 0u);
-				seg.range_offset[2] = seg.range_offset[1] + (trans_variable ? 6u * num_animated[1] : 0u);
+				seg.blob_format_offset = format_offset;
+				seg.blob_range_offset = range_offset;
+				seg.blob_animated_offset = animated_offset;
 
-				// Number of stored key frames, to bound the animated data (stripped segments store popcount(sample_indices) frames)
+				// Number of stored key frames (stripped segments store popcount(sample_indices) frames)
 				uint32_t stored_key_frames;
 				if (has_stripped)
 					stored_key_frames = uint32_t(__builtin_popcount(seg.sample_indices));
@@ -342,33 +463,71 @@ namespace aclb200
 						return "segment start indices are not sorted";
 					stored_key_frames = next - start;
 				}
-				if (!in_bounds(animated_offset, (uint64_t(pose_bit_size) * stored_key_frames + 7) / 8))
+				const uint64_t stream_bytes = (uint64_t(pose_bit_size) * stored_key_frames + 7) / 8;
+				if (!in_bounds(animated_offset, stream_bytes) || stream_bytes > 0xFFFFFF00ull)
 					return "animated data out of bounds";
+				seg.stream_bytes = uint32_t(stream_bytes);
+				const uint32_t key_frame_bytes = (pose_bit_size + 7) / 8;
+				out.max_key_frame_bytes = key_frame_bytes > out.max_key_frame_bytes ? key_frame_bytes : out.max_key_frame_bytes;
 
-				// Per sub-track bit offsets: the running sum of segment_animated_sampling_context_v0::animated_track_data_bit_offset
-				// (animated_track_cache.transform.h:598-599,653, cursors set up at :1240-1308)
-				uint32_t* entries = reinterpret_cast<uint32_t*>(out.index.data() + seg.entries_offset);
+				// Entries. Bit offsets are the running sum of segment_animated_sampling_context_v0::animated_track_data_bit_offset
+				// (animated_track_cache.transform.h:598-599,653; cursors set up at :1240-1308). Rotation metadata and segment range
+				// data are padded to groups of 4, translations / scales are not (:1264-1276,1296-1302).
+				seg.entries_offset = image.reserve(size_t(num_animated_total) * sizeof(Entry));
 				const uint8_t* format = blob + format_offset;
-				const bool variable[3] = { rot_variable, trans_variable, scale_variable };
+				const uint8_t* range = blob + range_offset;
 				const uint32_t kind_bit_offset[3] = { 0u, rotation_bit_size, rotation_bit_size + translation_bit_size };
-				const uint32_t kind_format_offset[3] = { 0u, rot_variable ? padded_rotations : 0u,
-					(rot_variable ? padded_rotations : 0u) + (trans_variable ? num_animated[1] : 0u) };
-				uint32_t entry_index = 0;
+				const uint32_t kind_format_offset[3] = { 0u, variable[0] ? padded_rotations : 0u,
+					(variable[0] ? padded_rotations : 0u) + (variable[1] ? num_animated[1] : 0u) };
+				uint32_t slot = 0;
 				for (uint32_t kind = 0; kind < 3; ++kind)
 				{
 					uint32_t bit_offset = kind_bit_offset[kind];
-					for (uint32_t j = 0; j < num_animated[kind]; ++j, ++entry_index)
+					for (uint32_t index = 0; index < num_animated[kind]; ++index, ++slot)
 					{
+						Entry entry = {};
 						uint32_t code, stream_bits;
+						entry.inv_max = 1.0F;
 						if (variable[kind])
 						{
-							const uint32_t stored = format[kind_format_offset[kind] + j];
+							const uint32_t stored = format[kind_format_offset[kind] + index];
+							// the 6 segment range bytes of this sub-track: min xyz, extent xyz
+							uint8_t r[6] = { 0, 0, 0, 0, 0, 0 };
+							if (num_segments > 1)
+							{
+								if (kind == 0)
+								{
+									// SOA per group of 4: min.xxxx min.yyyy min.zzzz extent.xxxx extent.yyyy extent.zzzz (:159)
+									const uint8_t* p = range + (index / 4) * 24 + (index % 4);
+									for (int c = 0; c < 6; ++c)
+										r[c] = p[4 * c];
+								}
+								else
+									std::memcpy(r, range + kind_format_offset[kind] * 6 + index * 6, 6);	// AOS (:936-940)
+							}
 							if (stored == 0)
 							{
-								code = 0;
-								stream_bits = 0;
+								// constant inside the segment, 16 bits per component (:552-587 rotations, unpack_vector3_u48_unsafe for vectors)
 								if (num_segments == 1)
 									return "constant bit rate inside a single segment clip";
+								uint32_t x, y, z;
+								if (kind == 0)
+								{
+									x = (uint32_t(r[0]) << 8) | r[1];
+									y = (uint32_t(r[2]) << 8) | r[3];
+									z = (uint32_t(r[4]) << 8) | r[5];
+								}
+								else
+								{
+									x = uint32_t(r[0]) | (uint32_t(r[1]) << 8);
+									y = uint32_t(r[2]) | (uint32_t(r[3]) << 8);
+									z = uint32_t(r[4]) | (uint32_t(r[5]) << 8);
+								}
+								code = 0;
+								stream_bits = 0;
+								entry.range_lo = x | (y << 16);
+								entry.range_hi = z;
+								entry.inv_max = 1.0F / 65535.0F;
 							}
 							else if (stored == raw_marker)
 							{
@@ -379,6 +538,9 @@ namespace aclb200
 							{
 								code = stored;
 								stream_bits = stored * 3;
+								entry.range_lo = uint32_t(r[0]) | (uint32_t(r[1]) << 8) | (uint32_t(r[2]) << 16) | (uint32_t(r[3]) << 24);
+								entry.range_hi = uint32_t(r[4]) | (uint32_t(r[5]) << 8);
+								entry.inv_max = inv_max_value(stored);
 							}
 							else
 								return "invalid per track bit count";
@@ -390,13 +552,19 @@ namespace aclb200
 						}
 						if (bit_offset >= (1u << 24))
 							return "key frame too large for the sub-track entry table";
-						entries[entry_index] = (bit_offset << 8) | code;
+						entry.offset_code = (bit_offset << 8) | code;
+						std::memcpy(image.at(seg.entries_offset) + size_t(slot) * sizeof(Entry), &entry, sizeof(entry));
 						bit_offset += stream_bits;
 					}
 					if (bit_offset > pose_bit_size && num_animated[kind] != 0)
 						return "sub-track bit widths exceed the animated pose size";
 				}
+
+				seg.stream_offset = append_stream(image, blob + animated_offset, size_t(stream_bytes));
+				std::memcpy(image.at(d.seg_table_offset) + size_t(segment) * sizeof(SegDesc), &seg, sizeof(seg));
 			}
+
+			d.image_size = image.reserve(0);
 			return std::string();
 		}
 	}
@@ -428,107 +596,87 @@ namespace aclb200
 		set->host_clips.resize(num_clips);
 		set->host_looping.resize(num_clips);
 
-		// Pass 1: parse, validate and size
-		std::vector<uint8_t> index_host;
-		uint64_t blob_bytes = 0;
-		uint32_t set_track_type = 0xFFFFFFFFu;
-		uint32_t max_tracks = 0, min_tracks = std::numeric_limits<uint32_t>::max(), max_animated_total = 0;
+		auto fail = [&](aclb200_status status, const std::string& message, uint32_t clip)
+		{
+			if (out_failed_clip != nullptr)
+				*out_failed_clip = clip;
+			delete set;
+			return set_error(context, status, message);
+		};
+
+		// Transcode in chunks so that a multi-GB clip set never needs a second full host copy: the clip images of a chunk are
+		// built in a staging vector and copied to the device when it fills up. Pass 1 only validates and sizes the device buffer.
+		const size_t staging_capacity = size_t(128) << 20;
+		std::vector<uint8_t> staging;
 		parse_result parsed;
+		uint64_t blob_bytes = 0, total_image_bytes = 0;
+		uint32_t set_track_type = 0xFFFFFFFFu;
+		uint32_t max_tracks = 0, min_tracks = std::numeric_limits<uint32_t>::max();
+
 		for (uint32_t clip = 0; clip < num_clips; ++clip)
 		{
 			bool unsupported = false;
-			const std::string error = parse_clip(get_blob(clip), sizes[clip], check_hash, parsed, unsupported);
+			staging.clear();
+			const std::string error = transcode_clip(get_blob(clip), sizes[clip], check_hash, staging, parsed, unsupported);
 			if (!error.empty())
-			{
-				if (out_failed_clip != nullptr)
-					*out_failed_clip = clip;
-				delete set;
-				return set_error(context, unsupported ? ACLB200_ERR_UNSUPPORTED : ACLB200_ERR_INVALID_CLIP,
-					"clip " + std::to_string(clip) + ": " + error);
-			}
+				return fail(unsupported ? ACLB200_ERR_UNSUPPORTED : ACLB200_ERR_INVALID_CLIP, "clip " + std::to_string(clip) + ": " + error, clip);
 			if (set_track_type == 0xFFFFFFFFu)
 				set_track_type = parsed.track_type;
 			else if (set_track_type != parsed.track_type)
-			{
-				if (out_failed_clip != nullptr)
-					*out_failed_clip = clip;
-				delete set;
-				return set_error(context, ACLB200_ERR_UNSUPPORTED, "clip " + std::to_string(clip) + ": a clip set holds a single track type");
-			}
+				return fail(ACLB200_ERR_UNSUPPORTED, "clip " + std::to_string(clip) + ": a clip set holds a single track type", clip);
 
 			ClipDesc& desc = set->host_clips[clip];
 			desc = parsed.desc;
-			desc.blob_offset = blob_bytes;
-			desc.index_offset = index_host.size();
-			blob_bytes += align_up64(desc.size, k_blob_alignment);
-			index_host.insert(index_host.end(), parsed.index.begin(), parsed.index.end());
-			index_host.resize(align_up64(index_host.size(), 16), 0);
+			desc.data_offset = total_image_bytes;
+			total_image_bytes += align_up64(desc.image_size, k_section_alignment);
+			blob_bytes += desc.size;
 			set->host_looping[clip] = parsed.looping_policy;
 			max_tracks = desc.num_tracks > max_tracks ? desc.num_tracks : max_tracks;
 			min_tracks = desc.num_tracks < min_tracks ? desc.num_tracks : min_tracks;
-			max_animated_total = desc.num_animated_total > max_animated_total ? desc.num_animated_total : max_animated_total;
+			if (parsed.track_type == k_track_qvvf)
+			{
+				for (int k = 0; k < 3; ++k)
+					set->max_animated[k] = desc.num_animated[k] > set->max_animated[k] ? desc.num_animated[k] : set->max_animated[k];
+				set->max_animated_total = desc.num_animated_total > set->max_animated_total ? desc.num_animated_total : set->max_animated_total;
+				set->max_key_frame_bytes = parsed.max_key_frame_bytes > set->max_key_frame_bytes ? parsed.max_key_frame_bytes : set->max_key_frame_bytes;
+			}
 		}
-		blob_bytes += k_tail_slack;
-		if (index_host.empty())
-			index_host.resize(16, 0);
+		total_image_bytes += k_stream_tail;
 
 		set->info.num_clips = num_clips;
 		set->info.track_type = set_track_type;
 		set->info.max_tracks = max_tracks;
 		set->info.min_tracks = min_tracks;
 		set->info.blob_bytes = blob_bytes;
-		set->info.index_bytes = index_host.size();
-		set->max_animated_total = max_animated_total;
+		set->info.index_bytes = total_image_bytes;
 
-		// Pass 2: device allocation + copies (clips go through a bounded staging buffer so that a multi-GB clip set does
-		// not need a second full host copy)
+		// pass 2: device allocation, transcode again chunk by chunk and copy
 		cudaError_t error = cudaSetDevice(context->device);
-		if (error == cudaSuccess) error = cudaMalloc(reinterpret_cast<void**>(&set->d_blobs), blob_bytes);
-		if (error == cudaSuccess) error = cudaMalloc(reinterpret_cast<void**>(&set->d_index), index_host.size());
+		if (error == cudaSuccess) error = cudaMalloc(reinterpret_cast<void**>(&set->d_data), total_image_bytes);
 		if (error == cudaSuccess) error = cudaMalloc(reinterpret_cast<void**>(&set->d_clips), sizeof(ClipDesc) * size_t(num_clips));
-		if (error == cudaSuccess) error = cudaMemset(set->d_blobs + (blob_bytes - k_tail_slack), 0, k_tail_slack);
+		if (error == cudaSuccess) error = cudaMemset(set->d_data + (total_image_bytes - k_stream_tail), 0, k_stream_tail);
 		if (error == cudaSuccess)
 		{
-			const size_t staging_capacity = size_t(64) << 20;
-			std::vector<uint8_t> staging;
-			staging.reserve(staging_capacity);
+			staging.clear();
 			uint64_t staging_base = 0;
-			auto flush = [&]() -> cudaError_t
-			{
-				if (staging.empty())
-					return cudaSuccess;
-				const cudaError_t e = cudaMemcpy(set->d_blobs + staging_base, staging.data(), staging.size(), cudaMemcpyHostToDevice);
-				staging_base += staging.size();
-				staging.clear();
-				return e;
-			};
 			for (uint32_t clip = 0; clip < num_clips && error == cudaSuccess; ++clip)
 			{
-				const ClipDesc& desc = set->host_clips[clip];
-				const size_t padded = size_t(align_up64(desc.size, k_blob_alignment));
-				if (staging.size() + padded > staging_capacity)
-					error = flush();
-				if (padded > staging_capacity)
+				bool unsupported = false;
+				transcode_clip(get_blob(clip), sizes[clip], false, staging, parsed, unsupported);
+				staging.resize(align_up64(staging.size(), k_section_alignment), 0);
+				if (staging.size() >= staging_capacity || clip + 1 == num_clips)
 				{
-					// a single huge clip: copy it directly
-					if (error == cudaSuccess) error = cudaMemcpy(set->d_blobs + desc.blob_offset, get_blob(clip), desc.size, cudaMemcpyHostToDevice);
-					if (error == cudaSuccess && padded > desc.size) error = cudaMemset(set->d_blobs + desc.blob_offset + desc.size, 0, padded - desc.size);
-					staging_base += padded;
-					continue;
+					error = cudaMemcpy(set->d_data + staging_base, staging.data(), staging.size(), cudaMemcpyHostToDevice);
+					staging_base += staging.size();
+					staging.clear();
 				}
-				const uint8_t* blob = get_blob(clip);
-				staging.insert(staging.end(), blob, blob + desc.size);
-				staging.resize(staging.size() + (padded - desc.size), 0);
 			}
-			if (error == cudaSuccess) error = flush();
 		}
-		if (error == cudaSuccess) error = cudaMemcpy(set->d_index, index_host.data(), index_host.size(), cudaMemcpyHostToDevice);
 		if (error == cudaSuccess) error = cudaMemcpy(set->d_clips, set->host_clips.data(), sizeof(ClipDesc) * size_t(num_clips), cudaMemcpyHostToDevice);
 		if (error != cudaSuccess)
 		{
 			const aclb200_status status = check_cuda(context, error, "upload_clips");
-			cudaFree(set->d_blobs);
-			cudaFree(set->d_index);
+			cudaFree(set->d_data);
 			cudaFree(set->d_clips);
 			delete set;
 			return status;

@@ -14,6 +14,7 @@ struct aclb200_context
 {
 	int device = 0;
 	int num_sms = 0;
+	int max_dynamic_smem = 0;
 	std::string last_error;
 	uint64_t launch_count = 0;
 
@@ -29,12 +30,13 @@ struct aclb200_clipset
 {
 	int device = 0;
 	aclb200_clipset_info info = {};
-	std::vector<aclb200::ClipDesc> host_clips;		// host mirror for the info queries and request validation
+	std::vector<aclb200::ClipDesc> host_clips;		// host mirror for the info queries
 	std::vector<uint32_t> host_looping;				// compressed_tracks::get_looping_policy() per clip
+	uint32_t max_animated[3] = { 0, 0, 0 };			// largest number of animated rotation / translation / scale sub-tracks of a clip
 	uint32_t max_animated_total = 0;
+	uint32_t max_key_frame_bytes = 0;				// largest ceil(animated_pose_bit_size / 8) of any segment
 
-	uint8_t* d_blobs = nullptr;
-	uint8_t* d_index = nullptr;
+	uint8_t* d_data = nullptr;
 	aclb200::ClipDesc* d_clips = nullptr;
 };
 
@@ -46,16 +48,20 @@ namespace aclb200
 	// One launch description shared by every kernel of the transform / scalar paths.
 	struct DecodeParams
 	{
-		const uint8_t* blobs;
-		const uint8_t* index;
+		const uint8_t* data;
 		const ClipDesc* clips;
 		const aclb200_request* requests;
 		const uint32_t* track_indices;		// decompress_track only
 		uint32_t num_requests;
 		uint32_t num_clips;
 		uint32_t max_tracks;
+		uint32_t max_animated[3];
 		uint32_t requests_per_block;		// whole requests handled by one thread block
-		uint32_t max_tracks_magic;			// floor(2^32 / max_tracks) + 1, turns j / max_tracks into a mulhi
+		uint32_t magic_tracks;				// floor(2^32 / d) + 1 for d = max_tracks / max_animated[0] / max(max_animated[1] + [2]):
+		uint32_t magic_rot;					// turns slot / d into a mulhi (0 when d == 1)
+		uint32_t magic_vec;
+		uint32_t stage_bytes;				// shared memory bytes reserved per staged key frame (0 = read the streams from global memory)
+		uint32_t smem_bytes;				// dynamic shared memory of the launch
 		uint8_t* out;
 		uint64_t pose_stride;
 		uint32_t bone_stride;				// 48 or 40 (transform), components * 4 (scalar)
@@ -77,10 +83,12 @@ namespace aclb200
 	};
 
 	// kernels.cu
+	void plan_launch(DecodeParams& params, uint32_t max_key_frame_bytes, int max_dynamic_smem);
 	cudaError_t launch_transform_decompress_tracks(const DecodeParams& params, uint32_t math_mode, cudaStream_t stream);
 	cudaError_t launch_transform_decompress_track(const DecodeParams& params, uint32_t math_mode, cudaStream_t stream);
 	cudaError_t launch_transform_debug_seek(const DecodeParams& params, aclb200_seek_state* d_out, cudaStream_t stream);
 	cudaError_t launch_transform_debug_unpack(const DecodeParams& params, uint32_t* d_out, cudaStream_t stream);
 	cudaError_t launch_scalar_decompress_tracks(const DecodeParams& params, cudaStream_t stream);
 	cudaError_t launch_scalar_decompress_track(const DecodeParams& params, cudaStream_t stream);
+	cudaError_t configure_kernels(int& max_dynamic_smem);
 }

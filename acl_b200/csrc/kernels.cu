@@ -6,12 +6,19 @@
 // (key frame / segment lookup, seek_v0, decompression/impl/decompression.transform.h:206-563), the variable bit
 // rate unpack (unpack_animated_quat / unpack_animated_vector3, animated_track_cache.transform.h:515-687,871-990),
 // the segment + clip range expansion (:157-350,391-466), the quaternion W reconstruction, the key frame
-// interpolation and normalisation (math/quatf.h:135-211) all happen in one pass, and the pose is written once.
+// interpolation and normalisation (math/quatf.h:135-211) all happen in one pass, and every pose byte is written once.
 //
 // Work decomposition (not the reference's: the CPU walks nine serial passes with running cursors):
-//   thread block  = `requests_per_block` whole requests; their seek runs once, on one thread each, into shared memory
-//   thread        = one bone of one request; the acceleration index built at upload (layout.h) gives it its
-//                   constant / animated ranks and bit offsets, so no thread depends on another one.
+//   thread block = `requests_per_block` whole requests.
+//     phase 1  one thread per request runs the seek, stores the request state in shared memory and asks the TMA unit
+//              (cp.async.bulk + mbarrier) to stage the request's two key frames -- a few hundred contiguous bytes of the
+//              packed segment stream each -- in shared memory.
+//     phase 2  while those copies fly: one thread per (request, bone) writes the constant and default sub-tracks.
+//     phase 3  one thread per (request, animated rotation sub-track): unpack both key frames from shared memory, expand,
+//              reconstruct W, lerp, normalise, store the quaternion.
+//     phase 4  one thread per (request, animated translation / scale sub-track).
+//   The passes are compacted per sub-track class, so warps do not diverge between animated and constant bones; the clip
+//   image built at upload (layout.h) gives every thread its operands with 16 byte loads and no dependency on other threads.
 //
 // Arithmetic contract (EXACT mode): every float operation is an IEEE-754 round-to-nearest mul/add/sub/sqrt/rcp
 // issued in the reference's order through __fmul_rn/__fadd_rn/... intrinsics, which nvcc never contracts into FMAs
@@ -25,7 +32,7 @@ namespace aclb200
 	{
 		constexpr uint32_t k_threads_per_block = 256;
 		constexpr uint32_t k_max_requests_per_block = 64;
-		constexpr uint32_t k_target_poses_per_block = 2048;
+		constexpr uint32_t k_target_items_per_block = 2048;
 
 		// ---------------------------------------------------------------------------------------------------
 		// exact float helpers
@@ -40,30 +47,72 @@ namespace aclb200
 		__device__ __forceinline__ float u2f(uint32_t v) { return __uint2float_rn(v); }
 
 		// ---------------------------------------------------------------------------------------------------
-		// per request state, written by one thread, read by every bone thread of the request
+		// TMA bulk copy + mbarrier (PTX ISA: cp.async.bulk, mbarrier)
 		// ---------------------------------------------------------------------------------------------------
-		struct ReqState
+		__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+		__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 		{
-			const uint8_t* blob;
-			const uint8_t* index;
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+
+		__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+		{
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+		}
+
+		__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+		{
+			asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+		}
+
+		__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+		{
+			uint32_t done;
+			do
+			{
+				asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+					: "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+			} while (!done);
+		}
+
+		// 1-D bulk tensor-less TMA copy global -> shared (SASS: UBLKCP); dst, src and bytes are multiples of 16
+		__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+		{
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+				:: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+		}
+
+		// ---------------------------------------------------------------------------------------------------
+		// per request state, written by one thread, read by every item thread of the request
+		// ---------------------------------------------------------------------------------------------------
+		struct alignas(16) ReqState
+		{
+			const uint8_t* image;
 			uint8_t* out;
 			float    alpha;
 			uint32_t num_tracks;			// 0 => nothing to decode (invalid request or empty clip)
 			uint32_t clip_flags;
 			uint32_t single_segment;
-			uint32_t kf_bit[2];				// key_frame_bit_offsets
-			uint32_t anim_off[2];
-			uint32_t entries_off[2];
-			uint32_t range_off[2][3];
-			uint32_t const_off[3];
-			uint32_t clip_range_off[3];
-			uint32_t num_animated[3];
-			uint32_t num_constant_rot;
+			uint32_t entries_off[2];		// image relative Entry tables of the two key frames' segments
+			uint32_t stream_off[2];			// image relative streams
+			uint32_t bit_base[2];			// staged: bit of the key frame inside its shared memory window; else key_frame_bit_offsets
+			uint32_t word_base[2];			// staged: first word of the window inside the block's staging area
+			uint32_t anim_off;
 			uint32_t bone_table_off;
-			// extras reported by the debug seek kernel
+			uint32_t const_rot_off;
+			uint32_t const_vec_off;
+			uint32_t num_animated[3];
+			uint32_t num_constant_trans;
+			// extras reported by the seek parity hook
 			float    sample_time;
+			uint32_t kf_bit[2];
 			uint32_t segment_index[2];
-			uint32_t format_off[2];
+			uint32_t blob_format_off[2];
+			uint32_t blob_range_off[2];
+			uint32_t blob_animated_off[2];
+			uint32_t pose_bits[2];
 			uint32_t looping_policy;
 		};
 
@@ -135,8 +184,7 @@ namespace aclb200
 			if (clip.num_tracks == 0)
 				return;
 
-			const uint8_t* blob = p.blobs + clip.blob_offset;
-			const uint8_t* index = p.index + clip.index_offset;
+			const uint8_t* image = p.data + clip.data_offset;
 
 			uint32_t looping_policy;
 			float duration;
@@ -150,7 +198,7 @@ namespace aclb200
 			float alpha;
 			find_key_frames(clip.num_samples, clip.sample_rate, sample_time, p.rounding_policy, looping_policy, key_frame0, key_frame1, alpha);
 
-			const SegDesc* segs = reinterpret_cast<const SegDesc*>(index + clip.seg_table_offset);
+			const SegDesc* segs = reinterpret_cast<const SegDesc*>(image + clip.seg_table_offset);
 			const bool stripped = (clip.flags & k_clip_stripped) != 0;
 			uint32_t segment_index0 = 0, segment_index1 = 0;
 			uint32_t segment_key_frame0, segment_key_frame1;
@@ -179,10 +227,9 @@ namespace aclb200
 			else
 			{
 				// :372-409, segment_start_indices ends with a 0xFFFFFFFF sentinel (compression/impl/write_segment_data.h:48-65)
-				const uint32_t* start_indices = reinterpret_cast<const uint32_t*>(blob + clip.start_indices_offset);
+				const uint32_t* start_indices = reinterpret_cast<const uint32_t*>(image + clip.start_indices_offset);
 				const uint32_t approx_segment_index = key_frame0 / clip.samples_per_segment;
 				const uint32_t start_segment_index = approx_segment_index > 0 ? approx_segment_index - 1 : 0;
-				uint32_t found_start = 0;
 				for (uint32_t i = 0; i < 4; ++i)
 				{
 					const uint32_t segment_index = start_segment_index + i;
@@ -194,11 +241,9 @@ namespace aclb200
 							segment_index1 = 0;
 						else
 							segment_index1 = key_frame1 < start ? segment_index0 : segment_index;
-						found_start = 1;
 						break;
 					}
 				}
-				(void)found_start;
 				const uint32_t start0 = start_indices[segment_index0];
 				const uint32_t start1 = start_indices[segment_index1];
 				segment_key_frame0 = key_frame0 - start0;
@@ -223,64 +268,64 @@ namespace aclb200
 			const SegDesc seg0 = segs[segment_index0];
 			const SegDesc seg1 = segs[segment_index1];
 
-			rs.blob = blob;
-			rs.index = index;
+			rs.image = image;
 			rs.alpha = alpha;
 			rs.num_tracks = clip.num_tracks;
 			rs.clip_flags = clip.flags;
 			rs.single_segment = segment_index0 == segment_index1;
 			rs.kf_bit[0] = segment_key_frame0 * seg0.pose_bit_size;				// :558-559
 			rs.kf_bit[1] = segment_key_frame1 * seg1.pose_bit_size;
-			rs.anim_off[0] = seg0.animated_offset;
-			rs.anim_off[1] = seg1.animated_offset;
+			rs.bit_base[0] = rs.kf_bit[0];
+			rs.bit_base[1] = rs.kf_bit[1];
+			rs.word_base[0] = rs.word_base[1] = 0;
+			rs.stream_off[0] = seg0.stream_offset;
+			rs.stream_off[1] = seg1.stream_offset;
 			rs.entries_off[0] = seg0.entries_offset;
 			rs.entries_off[1] = seg1.entries_offset;
-			for (int k = 0; k < 3; ++k)
-			{
-				rs.range_off[0][k] = seg0.range_offset[k];
-				rs.range_off[1][k] = seg1.range_offset[k];
-				rs.const_off[k] = clip.constant_offset[k];
-				rs.clip_range_off[k] = clip.clip_range_offset[k];
-				rs.num_animated[k] = clip.num_animated[k];
-			}
-			rs.num_constant_rot = clip.num_constant[0];
+			rs.pose_bits[0] = seg0.pose_bit_size;
+			rs.pose_bits[1] = seg1.pose_bit_size;
+			rs.anim_off = clip.anim_table_offset;
 			rs.bone_table_off = clip.bone_table_offset;
+			rs.const_rot_off = clip.const_rot_offset;
+			rs.const_vec_off = clip.const_vec_offset;
+			rs.num_constant_trans = clip.num_constant[1];
+			for (int k = 0; k < 3; ++k)
+				rs.num_animated[k] = clip.num_animated[k];
 			rs.sample_time = sample_time;
 			rs.segment_index[0] = segment_index0;
 			rs.segment_index[1] = segment_index1;
-			rs.format_off[0] = seg0.format_offset;
-			rs.format_off[1] = seg1.format_offset;
+			rs.blob_format_off[0] = seg0.blob_format_offset;
+			rs.blob_format_off[1] = seg1.blob_format_offset;
+			rs.blob_range_off[0] = seg0.blob_range_offset;
+			rs.blob_range_off[1] = seg1.blob_range_offset;
+			rs.blob_animated_off[0] = seg0.blob_animated_offset;
+			rs.blob_animated_off[1] = seg1.blob_animated_offset;
 			rs.looping_policy = looping_policy;
 		}
 
 		// ---------------------------------------------------------------------------------------------------
-		// bit stream reads. The animated stream of a segment starts on a 4 byte boundary of a 16 byte aligned
-		// blob, so it can be read as big-endian 32 bit words.
+		// bit stream reads. Streams are stored as byte-swapped 32-bit words (clipset.cpp append_stream): word i holds the
+		// stream bits [32 i, 32 i + 32) MSB first, so the 32 bits that start at any bit are one funnel shift of two words.
 		// ---------------------------------------------------------------------------------------------------
-		__device__ __forceinline__ uint32_t load_be_word(const uint32_t* words, uint32_t word_index)
+		template<bool STAGED>
+		__device__ __forceinline__ uint32_t read_bits32(const ReqState& rs, const uint32_t* s_stage, int k, uint32_t bit_offset)
 		{
-			return __byte_perm(__ldg(words + word_index), 0, 0x0123);
-		}
-
-		// The 32 bits that start at bit `bit_offset` of the stream (unpack_vector3_96_unsafe, math/vector4_packing.h:482-503)
-		__device__ __forceinline__ uint32_t read_bits32(const uint32_t* words, uint32_t bit_offset)
-		{
-			const uint32_t word_index = bit_offset >> 5;
-			const uint32_t hi = load_be_word(words, word_index);
-			const uint32_t lo = load_be_word(words, word_index + 1);
-			return __funnelshift_l(lo, hi, bit_offset & 31);
-		}
-
-		// `num_bits` (1..23) bits at `bit_offset` (unpack_vector3_uXX_unsafe, math/vector4_packing.h:947-971)
-		__device__ __forceinline__ uint32_t read_bits(const uint32_t* words, uint32_t bit_offset, uint32_t num_bits)
-		{
-			return read_bits32(words, bit_offset) >> (32 - num_bits);
-		}
-
-		// PackedTableEntry::max_value: 1.0F / float((1 << n) - 1) evaluated in float == correctly rounded reciprocal
-		__device__ __forceinline__ float inv_max_value(uint32_t num_bits)
-		{
-			return __frcp_rn(u2f((1u << num_bits) - 1u));
+			// unpack_vector3_96_unsafe, math/vector4_packing.h:482-503
+			const uint32_t bit = rs.bit_base[k] + bit_offset;
+			uint32_t hi, lo;
+			if (STAGED)
+			{
+				const uint32_t* w = s_stage + rs.word_base[k] + (bit >> 5);
+				hi = w[0];
+				lo = w[1];
+			}
+			else
+			{
+				const uint32_t* w = reinterpret_cast<const uint32_t*>(rs.image + rs.stream_off[k]) + (bit >> 5);
+				hi = __ldg(w);
+				lo = __ldg(w + 1);
+			}
+			return __funnelshift_l(lo, hi, bit & 31);
 		}
 
 		// quat_from_positive_w4, math/quatf.h:135-147
@@ -358,91 +403,83 @@ namespace aclb200
 		// ---------------------------------------------------------------------------------------------------
 		// sub-track decoders
 		// ---------------------------------------------------------------------------------------------------
+		__device__ __forceinline__ Entry load_entry(const ReqState& rs, int k, uint32_t slot)
+		{
+			const uint4 v = __ldg(reinterpret_cast<const uint4*>(rs.image + rs.entries_off[k]) + slot);
+			Entry e;
+			e.offset_code = v.x; e.range_lo = v.y; e.range_hi = v.z; e.inv_max = __uint_as_float(v.w);
+			return e;
+		}
 
-		// Raw integers of one animated sample: x, y, z (quantised integers or raw float bits), shared by the decode and by
-		// the parity hook. Returns the entry code.
-		__device__ __forceinline__ uint32_t unpack_sample_ints(const ReqState& rs, int k, uint32_t kind, uint32_t rank, uint32_t entry_index,
+		// Raw integers of one animated sample: x, y, z (quantised integers or raw float bits), shared by the decode and by the
+		// parity hook (unpack_animated_quat / unpack_animated_vector3 integer stage).
+		template<bool STAGED>
+		__device__ __forceinline__ void unpack_sample_ints(const ReqState& rs, const uint32_t* s_stage, int k, const Entry& e, bool four_components,
 			uint32_t& xi, uint32_t& yi, uint32_t& zi, uint32_t& wi)
 		{
-			const uint32_t entry = __ldg(reinterpret_cast<const uint32_t*>(rs.index + rs.entries_off[k]) + entry_index);
-			const uint32_t code = entry & 0xFFu;
-			const uint32_t bit_offset = (entry >> 8) + rs.kf_bit[k];
-			const uint32_t* words = reinterpret_cast<const uint32_t*>(rs.blob + rs.anim_off[k]);
+			const uint32_t code = e.offset_code & 0xFFu;
+			const uint32_t bit_offset = e.offset_code >> 8;
 			wi = 0;
 			if (code == 0)
 			{
-				if (kind == 0)
-				{
-					// constant inside the segment: 16 bits per component spread over the SOA range bytes of the group
-					// (unpack_animated_quat, animated_track_cache.transform.h:552-587)
-					const uint8_t* r = rs.blob + rs.range_off[k][0] + (rank >> 2) * 24 + (rank & 3);
-					xi = (uint32_t(__ldg(r + 0)) << 8) | __ldg(r + 4);
-					yi = (uint32_t(__ldg(r + 8)) << 8) | __ldg(r + 12);
-					zi = (uint32_t(__ldg(r + 16)) << 8) | __ldg(r + 20);
-				}
-				else
-				{
-					// unpack_vector3_u48_unsafe, math/vector4_packing.h:628-653: three native u16
-					const uint16_t* r = reinterpret_cast<const uint16_t*>(rs.blob + rs.range_off[k][kind] + rank * 6);
-					xi = __ldg(r + 0);
-					yi = __ldg(r + 1);
-					zi = __ldg(r + 2);
-				}
+				// constant inside the segment: the 3 x 16 bit sample was gathered from the segment range bytes at upload
+				// (animated_track_cache.transform.h:552-587; unpack_vector3_u48_unsafe, math/vector4_packing.h:628-653)
+				xi = e.range_lo & 0xFFFFu;
+				yi = e.range_lo >> 16;
+				zi = e.range_hi & 0xFFFFu;
 			}
 			else if (code & k_entry_raw)
 			{
-				xi = read_bits32(words, bit_offset);
-				yi = read_bits32(words, bit_offset + 32);
-				zi = read_bits32(words, bit_offset + 64);
-				if (kind == 0 && (rs.clip_flags & k_clip_rot_full))
-					wi = read_bits32(words, bit_offset + 96);
+				xi = read_bits32<STAGED>(rs, s_stage, k, bit_offset);
+				yi = read_bits32<STAGED>(rs, s_stage, k, bit_offset + 32);
+				zi = read_bits32<STAGED>(rs, s_stage, k, bit_offset + 64);
+				if (four_components)
+					wi = read_bits32<STAGED>(rs, s_stage, k, bit_offset + 96);
 			}
 			else
 			{
-				xi = read_bits(words, bit_offset, code);
-				yi = read_bits(words, bit_offset + code, code);
-				zi = read_bits(words, bit_offset + code * 2, code);
+				// unpack_vector3_uXX_unsafe, math/vector4_packing.h:947-971
+				const uint32_t shift = 32 - code;
+				xi = read_bits32<STAGED>(rs, s_stage, k, bit_offset) >> shift;
+				yi = read_bits32<STAGED>(rs, s_stage, k, bit_offset + code) >> shift;
+				zi = read_bits32<STAGED>(rs, s_stage, k, bit_offset + code * 2) >> shift;
 			}
-			return code;
 		}
 
 		// One animated rotation sample after range expansion and W reconstruction.
 		// SINGLE == false: decompress_tracks flavour (unpack_animated_quat + remap_segment_range_data4 + remap_clip_range_data4,
 		//                  animated_track_cache.transform.h:515-687,302-350,391-466): ignored ranges still multiply by 1 and add 0.
 		// SINGLE == true : decompress_track flavour (unpack_single_animated_quat, :689-869): ignored ranges are skipped.
-		template<bool SINGLE>
-		__device__ __forceinline__ void decode_animated_rotation(const ReqState& rs, int k, uint32_t rank, float out[4])
+		template<bool SINGLE, bool STAGED>
+		__device__ __forceinline__ void decode_animated_rotation(const ReqState& rs, const uint32_t* s_stage, int k, const Entry& e,
+			const float4& clip_extent, const float4& clip_min, float out[4])
 		{
+			const bool rot_full = (rs.clip_flags & k_clip_rot_full) != 0;
 			uint32_t xi, yi, zi, wi;
-			const uint32_t code = unpack_sample_ints(rs, k, 0, rank, rank, xi, yi, zi, wi);
+			unpack_sample_ints<STAGED>(rs, s_stage, k, e, rot_full, xi, yi, zi, wi);
+			const uint32_t code = e.offset_code & 0xFFu;
 
 			if (!(rs.clip_flags & k_clip_rot_variable))
 			{
 				out[0] = __uint_as_float(xi);
 				out[1] = __uint_as_float(yi);
 				out[2] = __uint_as_float(zi);
-				out[3] = (rs.clip_flags & k_clip_rot_full) ? __uint_as_float(wi) : quat_w(out[0], out[1], out[2]);
+				out[3] = rot_full ? __uint_as_float(wi) : quat_w(out[0], out[1], out[2]);
 				return;
 			}
 
 			float x, y, z;
-			bool ignore_segment = false, ignore_clip = false;
-			if (code == 0)
-			{
-				const float scale = 1.0f / 65535.0f;
-				x = fmul(u2f(xi), scale); y = fmul(u2f(yi), scale); z = fmul(u2f(zi), scale);
-				ignore_segment = true;
-			}
-			else if (code & k_entry_raw)
+			const bool is_raw = (code & k_entry_raw) != 0;
+			const bool ignore_segment = code == 0 || is_raw;
+			const bool ignore_clip = is_raw;
+			if (is_raw)
 			{
 				x = __uint_as_float(xi); y = __uint_as_float(yi); z = __uint_as_float(zi);
-				ignore_segment = true;
-				ignore_clip = true;
 			}
 			else
 			{
-				const float inv_max = inv_max_value(code);
-				x = fmul(u2f(xi), inv_max); y = fmul(u2f(yi), inv_max); z = fmul(u2f(zi), inv_max);
+				// code 0: 1 / 65535, else 1 / (2^code - 1) -- both stored in the entry
+				x = fmul(u2f(xi), e.inv_max); y = fmul(u2f(yi), e.inv_max); z = fmul(u2f(zi), e.inv_max);
 			}
 
 			if ((rs.clip_flags & k_clip_has_segments) && (!SINGLE || !ignore_segment))
@@ -450,11 +487,14 @@ namespace aclb200
 				float min_x = 0.0f, min_y = 0.0f, min_z = 0.0f, ext_x = 1.0f, ext_y = 1.0f, ext_z = 1.0f;
 				if (!ignore_segment)
 				{
-					// unpack_segment_range_data, :157-298: SOA bytes of the group of 4: min.xxxx min.yyyy min.zzzz extent.xxxx ...
-					const uint8_t* r = rs.blob + rs.range_off[k][0] + (rank >> 2) * 24 + (rank & 3);
+					// unpack_segment_range_data, :157-298: u8 * (1 / 255)
 					const float n = 1.0f / 255.0f;
-					min_x = fmul(u2f(__ldg(r + 0)), n); min_y = fmul(u2f(__ldg(r + 4)), n); min_z = fmul(u2f(__ldg(r + 8)), n);
-					ext_x = fmul(u2f(__ldg(r + 12)), n); ext_y = fmul(u2f(__ldg(r + 16)), n); ext_z = fmul(u2f(__ldg(r + 20)), n);
+					min_x = fmul(u2f(e.range_lo & 0xFFu), n);
+					min_y = fmul(u2f((e.range_lo >> 8) & 0xFFu), n);
+					min_z = fmul(u2f((e.range_lo >> 16) & 0xFFu), n);
+					ext_x = fmul(u2f(e.range_lo >> 24), n);
+					ext_y = fmul(u2f(e.range_hi & 0xFFu), n);
+					ext_z = fmul(u2f((e.range_hi >> 8) & 0xFFu), n);
 				}
 				x = fmuladd(x, ext_x, min_x);
 				y = fmuladd(y, ext_y, min_y);
@@ -463,16 +503,9 @@ namespace aclb200
 
 			if (!SINGLE || !ignore_clip)
 			{
-				float min_x = 0.0f, min_y = 0.0f, min_z = 0.0f, ext_x = 1.0f, ext_y = 1.0f, ext_z = 1.0f;
-				if (!ignore_clip)
-				{
-					// remap_clip_range_data4, :391-466: SOA per group of 4, the last group holds `group_size` lanes
-					const uint32_t group = rank >> 2;
-					const uint32_t group_size = min(rs.num_animated[0] - group * 4, 4u);
-					const float* r = reinterpret_cast<const float*>(rs.blob + rs.clip_range_off[0] + group * 96) + (rank & 3);
-					min_x = __ldg(r + group_size * 0); min_y = __ldg(r + group_size * 1); min_z = __ldg(r + group_size * 2);
-					ext_x = __ldg(r + group_size * 3); ext_y = __ldg(r + group_size * 4); ext_z = __ldg(r + group_size * 5);
-				}
+				// remap_clip_range_data4, :391-466
+				const float ext_x = ignore_clip ? 1.0f : clip_extent.x, ext_y = ignore_clip ? 1.0f : clip_extent.y, ext_z = ignore_clip ? 1.0f : clip_extent.z;
+				const float min_x = ignore_clip ? 0.0f : clip_min.x, min_y = ignore_clip ? 0.0f : clip_min.y, min_z = ignore_clip ? 0.0f : clip_min.z;
 				x = fmuladd(x, ext_x, min_x);
 				y = fmuladd(y, ext_y, min_y);
 				z = fmuladd(z, ext_z, min_z);
@@ -483,12 +516,13 @@ namespace aclb200
 		}
 
 		// unpack_animated_vector3 / unpack_single_animated_vector3, animated_track_cache.transform.h:871-990,992-1102
-		__device__ __forceinline__ void decode_animated_vector3(const ReqState& rs, int k, uint32_t kind, uint32_t rank, float out[3])
+		template<bool STAGED>
+		__device__ __forceinline__ void decode_animated_vector3(const ReqState& rs, const uint32_t* s_stage, int k, const Entry& e, bool variable,
+			const float4& clip_extent, const float4& clip_min, float out[3])
 		{
-			const uint32_t entry_index = rs.num_animated[0] + (kind == 2 ? rs.num_animated[1] : 0u) + rank;
 			uint32_t xi, yi, zi, wi;
-			const uint32_t code = unpack_sample_ints(rs, k, kind, rank, entry_index, xi, yi, zi, wi);
-			const bool variable = (rs.clip_flags & (kind == 1 ? k_clip_trans_variable : k_clip_scale_variable)) != 0;
+			unpack_sample_ints<STAGED>(rs, s_stage, k, e, false, xi, yi, zi, wi);
+			const uint32_t code = e.offset_code & 0xFFu;
 
 			if (!variable || (code & k_entry_raw))
 			{
@@ -496,59 +530,19 @@ namespace aclb200
 				return;
 			}
 
-			float x, y, z;
-			if (code == 0)
+			float x = fmul(u2f(xi), e.inv_max), y = fmul(u2f(yi), e.inv_max), z = fmul(u2f(zi), e.inv_max);
+			if (code != 0 && (rs.clip_flags & k_clip_has_segments))
 			{
-				const float scale = 1.0f / 65535.0f;
-				x = fmul(u2f(xi), scale); y = fmul(u2f(yi), scale); z = fmul(u2f(zi), scale);
+				// unpack_vector3_u24_unsafe min then extent, math/vector4_packing.h:781-818
+				const float n = 1.0f / 255.0f;
+				x = fmuladd(x, fmul(u2f(e.range_lo >> 24), n), fmul(u2f(e.range_lo & 0xFFu), n));
+				y = fmuladd(y, fmul(u2f(e.range_hi & 0xFFu), n), fmul(u2f((e.range_lo >> 8) & 0xFFu), n));
+				z = fmuladd(z, fmul(u2f((e.range_hi >> 8) & 0xFFu), n), fmul(u2f((e.range_lo >> 16) & 0xFFu), n));
 			}
-			else
-			{
-				const float inv_max = inv_max_value(code);
-				x = fmul(u2f(xi), inv_max); y = fmul(u2f(yi), inv_max); z = fmul(u2f(zi), inv_max);
-				if (rs.clip_flags & k_clip_has_segments)
-				{
-					// unpack_vector3_u24_unsafe min then extent, math/vector4_packing.h:781-818
-					const uint8_t* r = rs.blob + rs.range_off[k][kind] + rank * 6;
-					const float n = 1.0f / 255.0f;
-					x = fmuladd(x, fmul(u2f(__ldg(r + 3)), n), fmul(u2f(__ldg(r + 0)), n));
-					y = fmuladd(y, fmul(u2f(__ldg(r + 4)), n), fmul(u2f(__ldg(r + 1)), n));
-					z = fmuladd(z, fmul(u2f(__ldg(r + 5)), n), fmul(u2f(__ldg(r + 2)), n));
-				}
-			}
-
-			// clip range: min xyz then extent xyz, 24 bytes per sub-track (:949-958)
-			const float* r = reinterpret_cast<const float*>(rs.blob + rs.clip_range_off[kind] + rank * 24);
-			out[0] = fmuladd(x, __ldg(r + 3), __ldg(r + 0));
-			out[1] = fmuladd(y, __ldg(r + 4), __ldg(r + 1));
-			out[2] = fmuladd(z, __ldg(r + 5), __ldg(r + 2));
-		}
-
-		// constant_track_cache_v0::unpack_rotation_group / unpack_rotation_within_group, constant_track_cache.transform.h:112-205,232-264
-		template<int NORM, bool SINGLE>
-		__device__ __forceinline__ void decode_constant_rotation(const ReqState& rs, uint32_t rank, float out[4])
-		{
-			if (rs.clip_flags & k_clip_rot_full)
-			{
-				const float* r = reinterpret_cast<const float*>(rs.blob + rs.const_off[0]) + rank * 4;
-				out[0] = __ldg(r + 0); out[1] = __ldg(r + 1); out[2] = __ldg(r + 2); out[3] = __ldg(r + 3);
-				return;
-			}
-			const uint32_t group = rank >> 2;
-			const uint32_t group_size = min(rs.num_constant_rot - group * 4, 4u);
-			const float* r = reinterpret_cast<const float*>(rs.blob + rs.const_off[0] + group * 48) + (rank & 3);
-			const float x = __ldg(r + group_size * 0);
-			const float y = __ldg(r + group_size * 1);
-			const float z = __ldg(r + group_size * 2);
-			out[0] = x; out[1] = y; out[2] = z;
-			out[3] = quat_w(x, y, z);
-			if (NORM == ACLB200_NORMALIZE_ALWAYS)
-			{
-				if (SINGLE)
-					rtm_quat_normalize(out);
-				else
-					quat_normalize(out);
-			}
+			// clip range (:949-958)
+			out[0] = fmuladd(x, clip_extent.x, clip_min.x);
+			out[1] = fmuladd(y, clip_extent.y, clip_min.y);
+			out[2] = fmuladd(z, clip_extent.z, clip_min.z);
 		}
 
 		// should_interpolate_samples, decompression_context.transform.h:191-200
@@ -591,191 +585,321 @@ namespace aclb200
 			return true;
 		}
 
-		// One bone of one request: the three sub-tracks of decompress_tracks_v0 (decompression.transform.h:1526-1737) or
-		// decompress_track_v0 (:1753-2050, SINGLE).
-		template<int NORM, bool PER_TRACK, bool SINGLE>
-		__device__ __forceinline__ void decode_bone(const DecodeParams& p, const ReqState& rs, uint32_t bone, uint8_t* out_bone)
+		// ---- the device track_writer: write_rotation / write_translation / write_scale ----
+		__device__ __forceinline__ void write_rotation(uint32_t layout, uint8_t* bone, const float q[4])
 		{
-			const uint64_t desc = __ldg(reinterpret_cast<const unsigned long long*>(rs.index + rs.bone_table_off) + bone);
+			if (layout == ACLB200_LAYOUT_QVV48)
+				*reinterpret_cast<float4*>(bone) = make_float4(q[0], q[1], q[2], q[3]);
+			else
+			{
+				float2* dst = reinterpret_cast<float2*>(bone);		// 40 byte bones are 8 byte aligned
+				dst[0] = make_float2(q[0], q[1]);
+				dst[1] = make_float2(q[2], q[3]);
+			}
+		}
+
+		__device__ __forceinline__ void write_vector(uint32_t layout, uint8_t* bone, uint32_t kind, const float v[3])
+		{
+			if (layout == ACLB200_LAYOUT_QVV48)
+				*reinterpret_cast<float4*>(bone + 16 * kind) = make_float4(v[0], v[1], v[2], 0.0f);
+			else if (kind == 1)
+			{
+				*reinterpret_cast<float2*>(bone + 16) = make_float2(v[0], v[1]);
+				*reinterpret_cast<float*>(bone + 24) = v[2];
+			}
+			else
+			{
+				*reinterpret_cast<float*>(bone + 28) = v[0];
+				*reinterpret_cast<float2*>(bone + 32) = make_float2(v[1], v[2]);
+			}
+		}
+
+		// Interpolation of two decoded rotation samples: unpack_rotation_group, animated_track_cache.transform.h:1463-1474,1477-1661
+		// (SINGLE: unpack_rotation_within_group, :1709-1765)
+		template<int NORM, bool PER_TRACK, bool SINGLE>
+		__device__ __forceinline__ void interpolate_rotation(const DecodeParams& p, uint32_t clip_flags, float s0[4], float s1[4], float alpha, uint32_t policy, float rotation[4])
+		{
+			const bool interpolate = should_interpolate(p, clip_flags, alpha);
+			if (SINGLE)
+			{
+				if (interpolate)
+					rtm_quat_lerp(s0, s1, alpha, NORM >= ACLB200_NORMALIZE_LERP_ONLY, rotation);
+				else
+				{
+#pragma unroll
+					for (int i = 0; i < 4; ++i)
+						rotation[i] = alpha <= 0.0f ? s0[i] : s1[i];
+					if (NORM == ACLB200_NORMALIZE_ALWAYS && !(clip_flags & k_clip_rot_full))
+						rtm_quat_normalize(rotation);
+				}
+				return;
+			}
+
+			if (NORM == ACLB200_NORMALIZE_ALWAYS && !(clip_flags & k_clip_rot_full) && (PER_TRACK || !interpolate))
+			{
+				quat_normalize(s0);
+				quat_normalize(s1);
+			}
+
+			if (PER_TRACK && policy == ACLB200_ROUND_FLOOR)
+			{
+#pragma unroll
+				for (int i = 0; i < 4; ++i) rotation[i] = s0[i];
+			}
+			else if (PER_TRACK && policy == ACLB200_ROUND_CEIL)
+			{
+#pragma unroll
+				for (int i = 0; i < 4; ++i) rotation[i] = s1[i];
+			}
+			else if (PER_TRACK && policy == ACLB200_ROUND_NEAREST)
+			{
+#pragma unroll
+				for (int i = 0; i < 4; ++i) rotation[i] = alpha < 0.5f ? s0[i] : s1[i];
+			}
+			else if (PER_TRACK || interpolate)
+			{
+				quat_lerp(s0, s1, alpha, rotation);
+				if (NORM >= ACLB200_NORMALIZE_LERP_ONLY)
+					quat_normalize(rotation);
+			}
+			else
+			{
+#pragma unroll
+				for (int i = 0; i < 4; ++i) rotation[i] = alpha <= 0.0f ? s0[i] : s1[i];
+			}
+		}
+
+		// One animated rotation sub-track of one request (phase 3)
+		template<int NORM, bool PER_TRACK, bool SINGLE, bool STAGED>
+		__device__ __forceinline__ uint32_t animated_rotation(const DecodeParams& p, const ReqState& rs, const uint32_t* s_stage, uint32_t rank, float alpha_in, float rotation[4])
+		{
+			const float4* anim = reinterpret_cast<const float4*>(rs.image + rs.anim_off) + size_t(rank) * 2;
+			const float4 clip_extent = __ldg(anim + 0);		// .w carries the bone index
+			const float4 clip_min = __ldg(anim + 1);
+			const uint32_t bone = __float_as_uint(clip_extent.w);
+			const Entry e0 = load_entry(rs, 0, rank);
+			const Entry e1 = rs.single_segment ? e0 : load_entry(rs, 1, rank);
+
+			float s0[4], s1[4];
+			decode_animated_rotation<SINGLE, STAGED>(rs, s_stage, 0, e0, clip_extent, clip_min, s0);
+			decode_animated_rotation<SINGLE, STAGED>(rs, s_stage, 1, e1, clip_extent, clip_min, s1);
+
 			const uint32_t policy = PER_TRACK ? track_rounding_policy(p, bone) : ACLB200_ROUND_NONE;
-			const float alpha = (SINGLE && PER_TRACK) ? apply_rounding_policy(rs.alpha, policy) : rs.alpha;	// :1975-1983
+			const float alpha = (SINGLE && PER_TRACK) ? apply_rounding_policy(alpha_in, policy) : alpha_in;	// :1975-1983
+			interpolate_rotation<NORM, PER_TRACK, SINGLE>(p, rs.clip_flags, s0, s1, alpha, policy, rotation);
+			return bone;
+		}
 
-			float rotation[4];
-			float translation[4];
-			float scale[4];
-			bool write_rotation = true, write_translation = true, write_scale = true;
+		// One animated translation (kind 1) or scale (kind 2) sub-track of one request (phase 4):
+		// unpack_translation_group / consume_translation, animated_track_cache.transform.h:1774-1836,1889-1894
+		template<bool PER_TRACK, bool SINGLE, bool STAGED>
+		__device__ __forceinline__ uint32_t animated_vector(const DecodeParams& p, const ReqState& rs, const uint32_t* s_stage, uint32_t kind, uint32_t rank, float alpha_in, float value[3])
+		{
+			const uint32_t slot = rs.num_animated[0] + (kind == 2 ? rs.num_animated[1] : 0u) + rank;
+			const float4* anim = reinterpret_cast<const float4*>(rs.image + rs.anim_off) + size_t(slot) * 2;
+			const float4 clip_extent = __ldg(anim + 0);
+			const float4 clip_min = __ldg(anim + 1);
+			const uint32_t bone = __float_as_uint(clip_extent.w);
+			const Entry e0 = load_entry(rs, 0, slot);
+			const Entry e1 = rs.single_segment ? e0 : load_entry(rs, 1, slot);
+			const bool variable = (rs.clip_flags & (kind == 1 ? k_clip_trans_variable : k_clip_scale_variable)) != 0;
 
-			// ---- rotation ----
+			float s0[3], s1[3];
+			decode_animated_vector3<STAGED>(rs, s_stage, 0, e0, variable, clip_extent, clip_min, s0);
+			decode_animated_vector3<STAGED>(rs, s_stage, 1, e1, variable, clip_extent, clip_min, s1);
+
+			const uint32_t policy = PER_TRACK ? track_rounding_policy(p, bone) : ACLB200_ROUND_NONE;
+			const float alpha = (SINGLE && PER_TRACK) ? apply_rounding_policy(alpha_in, policy) : alpha_in;
+#pragma unroll
+			for (int i = 0; i < 3; ++i)
+			{
+				if (!SINGLE && PER_TRACK && policy == ACLB200_ROUND_FLOOR)
+					value[i] = s0[i];
+				else if (!SINGLE && PER_TRACK && policy == ACLB200_ROUND_CEIL)
+					value[i] = s1[i];
+				else if (!SINGLE && PER_TRACK && policy == ACLB200_ROUND_NEAREST)
+					value[i] = alpha < 0.5f ? s0[i] : s1[i];
+				else
+					value[i] = lerp(s0[i], s1[i], alpha);
+			}
+			return bone;
+		}
+
+		// Constant and default sub-tracks of one bone (phase 2): unpack_default_* / unpack_constant_*_sub_tracks,
+		// decompression.transform.h:574-748,881-1072,1201-1430; constant rotations had their W reconstructed (and normalised) at upload
+		template<int NORM, bool SINGLE>
+		__device__ __forceinline__ void constant_sub_tracks(const DecodeParams& p, const ReqState& rs, uint32_t bone, uint64_t desc, uint8_t* out_bone)
+		{
+			// rotation
 			{
 				const uint32_t type = uint32_t(desc) & 3;
 				const uint32_t rank = (uint32_t(desc) >> 2) & k_bone_index_mask;
+				float q[4];
 				if (type == 0)
-					write_rotation = default_value(p, 0, bone, rs.clip_flags, rotation);
-				else if (type == 1)
-					decode_constant_rotation<NORM, SINGLE>(rs, rank, rotation);
-				else
 				{
-					float s0[4], s1[4];
-					decode_animated_rotation<SINGLE>(rs, 0, rank, s0);
-					decode_animated_rotation<SINGLE>(rs, 1, rank, s1);
-					const bool interpolate = should_interpolate(p, rs.clip_flags, alpha);
-
-					if (SINGLE)
+					if (default_value(p, 0, bone, rs.clip_flags, q))
+						write_rotation(p.layout, out_bone, q);
+				}
+				else if (type == 1)
+				{
+					const float4* table = reinterpret_cast<const float4*>(rs.image + rs.const_rot_off) + size_t(rank) * 2;
+					if (SINGLE && NORM == ACLB200_NORMALIZE_ALWAYS && !(rs.clip_flags & k_clip_rot_full))
 					{
-						// unpack_rotation_within_group, animated_track_cache.transform.h:1709-1765
-						if (interpolate)
-							rtm_quat_lerp(s0, s1, alpha, NORM >= ACLB200_NORMALIZE_LERP_ONLY, rotation);
-						else
-						{
-#pragma unroll
-							for (int i = 0; i < 4; ++i)
-								rotation[i] = alpha <= 0.0f ? s0[i] : s1[i];
-							if (NORM == ACLB200_NORMALIZE_ALWAYS && !(rs.clip_flags & k_clip_rot_full))
-								rtm_quat_normalize(rotation);
-						}
+						// unpack_rotation_within_group normalises with rtm::quat_normalize, constant_track_cache.transform.h:255-258
+						const float4 v = __ldg(table);
+						q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
+						rtm_quat_normalize(q);
 					}
 					else
 					{
-						// unpack_rotation_group, :1463-1474,1477-1661
-						if (NORM == ACLB200_NORMALIZE_ALWAYS && !(rs.clip_flags & k_clip_rot_full) && (PER_TRACK || !interpolate))
-						{
-							quat_normalize(s0);
-							quat_normalize(s1);
-						}
-
-						if (PER_TRACK && policy == ACLB200_ROUND_FLOOR)
-						{
-#pragma unroll
-							for (int i = 0; i < 4; ++i) rotation[i] = s0[i];
-						}
-						else if (PER_TRACK && policy == ACLB200_ROUND_CEIL)
-						{
-#pragma unroll
-							for (int i = 0; i < 4; ++i) rotation[i] = s1[i];
-						}
-						else if (PER_TRACK && policy == ACLB200_ROUND_NEAREST)
-						{
-#pragma unroll
-							for (int i = 0; i < 4; ++i) rotation[i] = alpha < 0.5f ? s0[i] : s1[i];
-						}
-						else if (PER_TRACK || interpolate)
-						{
-							quat_lerp(s0, s1, alpha, rotation);
-							if (NORM >= ACLB200_NORMALIZE_LERP_ONLY)
-								quat_normalize(rotation);
-						}
-						else
-						{
-#pragma unroll
-							for (int i = 0; i < 4; ++i) rotation[i] = alpha <= 0.0f ? s0[i] : s1[i];
-						}
+						const float4 v = __ldg(table + (NORM == ACLB200_NORMALIZE_ALWAYS ? 1 : 0));
+						q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
 					}
+					write_rotation(p.layout, out_bone, q);
 				}
 			}
-
-			// ---- translation, scale ----
+			// translation, scale
 #pragma unroll
 			for (uint32_t kind = 1; kind <= 2; ++kind)
 			{
-				float* value = kind == 1 ? translation : scale;
-				bool written = true;
 				const uint32_t bits = uint32_t(desc >> (k_bone_kind_shift * kind));
 				// clips without scale: every bone takes the default (decompression.transform.h:1653-1680,1806-1822)
 				const uint32_t type = (kind == 2 && !(rs.clip_flags & k_clip_has_scale)) ? 0u : (bits & 3);
 				const uint32_t rank = (bits >> 2) & k_bone_index_mask;
+				float v[4];
 				if (type == 0)
-					written = default_value(p, kind, bone, rs.clip_flags, value);
+				{
+					if (default_value(p, kind, bone, rs.clip_flags, v))
+						write_vector(p.layout, out_bone, kind, v);
+				}
 				else if (type == 1)
 				{
-					const float* r = reinterpret_cast<const float*>(rs.blob + rs.const_off[kind]) + rank * 3;
-					value[0] = __ldg(r + 0); value[1] = __ldg(r + 1); value[2] = __ldg(r + 2);
-					value[3] = 0.0f;
+					const float4 c = __ldg(reinterpret_cast<const float4*>(rs.image + rs.const_vec_off) + (kind == 2 ? rs.num_constant_trans : 0u) + rank);
+					v[0] = c.x; v[1] = c.y; v[2] = c.z;
+					write_vector(p.layout, out_bone, kind, v);
 				}
-				else
-				{
-					float s0[3], s1[3];
-					decode_animated_vector3(rs, 0, kind, rank, s0);
-					decode_animated_vector3(rs, 1, kind, rank, s1);
-#pragma unroll
-					for (int i = 0; i < 3; ++i)
-					{
-						// unpack_translation_group / consume_translation, animated_track_cache.transform.h:1774-1836,1889-1894
-						if (!SINGLE && PER_TRACK && policy == ACLB200_ROUND_FLOOR)
-							value[i] = s0[i];
-						else if (!SINGLE && PER_TRACK && policy == ACLB200_ROUND_CEIL)
-							value[i] = s1[i];
-						else if (!SINGLE && PER_TRACK && policy == ACLB200_ROUND_NEAREST)
-							value[i] = alpha < 0.5f ? s0[i] : s1[i];
-						else
-							value[i] = lerp(s0[i], s1[i], alpha);
-					}
-					value[3] = 0.0f;
-				}
-				if (kind == 1) write_translation = written; else write_scale = written;
 			}
+		}
 
-			// ---- the device track_writer: write_rotation / write_translation / write_scale ----
-			if (p.layout == ACLB200_LAYOUT_QVV48)
-			{
-				float4* dst = reinterpret_cast<float4*>(out_bone);
-				if (write_rotation) dst[0] = make_float4(rotation[0], rotation[1], rotation[2], rotation[3]);
-				if (write_translation) dst[1] = make_float4(translation[0], translation[1], translation[2], 0.0f);
-				if (write_scale) dst[2] = make_float4(scale[0], scale[1], scale[2], 0.0f);
-			}
-			else
-			{
-				float2* dst = reinterpret_cast<float2*>(out_bone);		// 40 byte bones are 8 byte aligned
-				if (write_rotation && write_translation && write_scale)
-				{
-					dst[0] = make_float2(rotation[0], rotation[1]);
-					dst[1] = make_float2(rotation[2], rotation[3]);
-					dst[2] = make_float2(translation[0], translation[1]);
-					dst[3] = make_float2(translation[2], scale[0]);
-					dst[4] = make_float2(scale[1], scale[2]);
-				}
-				else
-				{
-					float* f = reinterpret_cast<float*>(out_bone);
-					if (write_rotation) { f[0] = rotation[0]; f[1] = rotation[1]; f[2] = rotation[2]; f[3] = rotation[3]; }
-					if (write_translation) { f[4] = translation[0]; f[5] = translation[1]; f[6] = translation[2]; }
-					if (write_scale) { f[7] = scale[0]; f[8] = scale[1]; f[9] = scale[2]; }
-				}
-			}
+		__device__ __forceinline__ uint32_t fast_div(uint32_t value, uint32_t magic)
+		{
+			return magic != 0 ? __umulhi(value, magic) : value;
 		}
 
 		// ---------------------------------------------------------------------------------------------------
 		// kernels
 		// ---------------------------------------------------------------------------------------------------
-		template<int NORM, bool PER_TRACK>
+		template<int NORM, bool PER_TRACK, bool STAGED>
 		__global__ void __launch_bounds__(k_threads_per_block)
 		transform_decompress_tracks_kernel(const DecodeParams p)
 		{
+			extern __shared__ __align__(16) uint8_t s_dynamic[];
 			__shared__ ReqState s_req[k_max_requests_per_block];
+			__shared__ __align__(8) uint64_t s_barrier;
+			const uint32_t* s_stage = reinterpret_cast<const uint32_t*>(s_dynamic);
 
 			const uint32_t first_request = blockIdx.x * p.requests_per_block;
 			const uint32_t num_requests = min(p.requests_per_block, p.num_requests - first_request);
 
+			if (STAGED)
+			{
+				if (threadIdx.x == 0)
+					mbar_init(&s_barrier, num_requests);
+				__syncthreads();
+			}
+
+			// ---- phase 1: seek + stage the two key frames ----
 			if (threadIdx.x < num_requests)
 			{
 				ReqState rs;
 				seek_transform(p, first_request + threadIdx.x, rs);
 				rs.out = p.out + uint64_t(first_request + threadIdx.x) * p.pose_stride;
+				if (STAGED)
+				{
+					if (rs.num_tracks != 0 && (rs.num_animated[0] | rs.num_animated[1] | rs.num_animated[2]) != 0)
+					{
+						uint32_t src_byte[2], bytes[2];
+#pragma unroll
+						for (int k = 0; k < 2; ++k)
+						{
+							src_byte[k] = (rs.kf_bit[k] >> 3) & ~15u;
+							rs.bit_base[k] = rs.kf_bit[k] - src_byte[k] * 8;
+							rs.word_base[k] = (threadIdx.x * 2 + k) * (p.stage_bytes >> 2);
+							bytes[k] = min((((rs.bit_base[k] + rs.pose_bits[k] + 7) >> 3) + 8 + 15) & ~15u, p.stage_bytes);
+						}
+						mbar_arrive_expect_tx(&s_barrier, bytes[0] + bytes[1]);
+#pragma unroll
+						for (int k = 0; k < 2; ++k)
+							bulk_copy_g2s(s_dynamic + size_t(rs.word_base[k]) * 4, rs.image + rs.stream_off[k] + src_byte[k], bytes[k], &s_barrier);
+					}
+					else
+						mbar_arrive(&s_barrier);
+				}
 				s_req[threadIdx.x] = rs;
 			}
 			__syncthreads();
 
-			const uint32_t num_slots = num_requests * p.max_tracks;
-			for (uint32_t slot = threadIdx.x; slot < num_slots; slot += k_threads_per_block)
+			// ---- phase 2: constant and default sub-tracks, one thread per (request, bone) ----
 			{
-				const uint32_t local_request = p.max_tracks_magic != 0 ? __umulhi(slot, p.max_tracks_magic) : slot;
-				const uint32_t bone = slot - local_request * p.max_tracks;
-				const ReqState& rs = s_req[local_request];
-				if (bone >= rs.num_tracks)
-					continue;
-				decode_bone<NORM, PER_TRACK, false>(p, rs, bone, rs.out + size_t(bone) * p.bone_stride);
+				const uint32_t num_slots = num_requests * p.max_tracks;
+				for (uint32_t slot = threadIdx.x; slot < num_slots; slot += k_threads_per_block)
+				{
+					const uint32_t local_request = fast_div(slot, p.magic_tracks);
+					const uint32_t bone = slot - local_request * p.max_tracks;
+					const ReqState& rs = s_req[local_request];
+					if (bone >= rs.num_tracks)
+						continue;
+					const uint64_t desc = __ldg(reinterpret_cast<const unsigned long long*>(rs.image + rs.bone_table_off) + bone);
+					constant_sub_tracks<NORM, false>(p, rs, bone, desc, rs.out + size_t(bone) * p.bone_stride);
+				}
+			}
+
+			if (STAGED)
+				mbar_wait(&s_barrier, 0);
+
+			// ---- phase 3: animated rotations, one thread per (request, animated rotation sub-track) ----
+			if (p.max_animated[0] != 0)
+			{
+				const uint32_t num_slots = num_requests * p.max_animated[0];
+				for (uint32_t slot = threadIdx.x; slot < num_slots; slot += k_threads_per_block)
+				{
+					const uint32_t local_request = fast_div(slot, p.magic_rot);
+					const uint32_t rank = slot - local_request * p.max_animated[0];
+					const ReqState& rs = s_req[local_request];
+					if (rs.num_tracks == 0 || rank >= rs.num_animated[0])
+						continue;
+					float rotation[4];
+					const uint32_t bone = animated_rotation<NORM, PER_TRACK, false, STAGED>(p, rs, s_stage, rank, rs.alpha, rotation);
+					write_rotation(p.layout, rs.out + size_t(bone) * p.bone_stride, rotation);
+				}
+			}
+
+			// ---- phase 4: animated translations then scales ----
+			const uint32_t max_vectors = p.max_animated[1] + p.max_animated[2];
+			if (max_vectors != 0)
+			{
+				const uint32_t num_slots = num_requests * max_vectors;
+				for (uint32_t slot = threadIdx.x; slot < num_slots; slot += k_threads_per_block)
+				{
+					const uint32_t local_request = fast_div(slot, p.magic_vec);
+					uint32_t rank = slot - local_request * max_vectors;
+					const ReqState& rs = s_req[local_request];
+					uint32_t kind = 1;
+					if (rank >= p.max_animated[1])
+					{
+						rank -= p.max_animated[1];
+						kind = 2;
+					}
+					if (rs.num_tracks == 0 || rank >= rs.num_animated[kind])
+						continue;
+					float value[3];
+					const uint32_t bone = animated_vector<PER_TRACK, false, STAGED>(p, rs, s_stage, kind, rank, rs.alpha, value);
+					write_vector(p.layout, rs.out + size_t(bone) * p.bone_stride, kind, value);
+				}
 			}
 		}
 
+		// decompress_track_v0, decompression.transform.h:1753-2050: one thread per request, one bone each
 		template<int NORM, bool PER_TRACK>
 		__global__ void __launch_bounds__(128)
 		transform_decompress_track_kernel(const DecodeParams p)
@@ -787,8 +911,28 @@ namespace aclb200
 			seek_transform(p, request, rs);
 			const uint32_t bone = p.track_indices[request];
 			if (bone >= rs.num_tracks)
-				return;		// decompress_track_v0 :1766-1768: invalid track index, nothing is written
-			decode_bone<NORM, PER_TRACK, true>(p, rs, bone, p.out + uint64_t(request) * p.bone_stride);
+				return;		// :1766-1768: invalid track index, nothing is written
+			uint8_t* out_bone = p.out + uint64_t(request) * p.bone_stride;
+			const uint64_t desc = __ldg(reinterpret_cast<const unsigned long long*>(rs.image + rs.bone_table_off) + bone);
+			constant_sub_tracks<NORM, true>(p, rs, bone, desc, out_bone);
+
+			if ((uint32_t(desc) & 3) == 2)
+			{
+				float rotation[4];
+				animated_rotation<NORM, PER_TRACK, true, false>(p, rs, nullptr, (uint32_t(desc) >> 2) & k_bone_index_mask, rs.alpha, rotation);
+				write_rotation(p.layout, out_bone, rotation);
+			}
+#pragma unroll
+			for (uint32_t kind = 1; kind <= 2; ++kind)
+			{
+				const uint32_t bits = uint32_t(desc >> (k_bone_kind_shift * kind));
+				if ((bits & 3) == 2 && (kind == 1 || (rs.clip_flags & k_clip_has_scale)))
+				{
+					float value[3];
+					animated_vector<PER_TRACK, true, false>(p, rs, nullptr, kind, (bits >> 2) & k_bone_index_mask, rs.alpha, value);
+					write_vector(p.layout, out_bone, kind, value);
+				}
+			}
 		}
 
 		__global__ void __launch_bounds__(128)
@@ -810,9 +954,9 @@ namespace aclb200
 				{
 					st.key_frame_bit_offsets[k] = rs.kf_bit[k];
 					st.segment_indices[k] = rs.segment_index[k];
-					st.animated_offsets[k] = rs.anim_off[k];
-					st.format_offsets[k] = rs.format_off[k];
-					st.range_offsets[k] = rs.range_off[k][0];
+					st.animated_offsets[k] = rs.blob_animated_off[k];
+					st.format_offsets[k] = rs.blob_format_off[k];
+					st.range_offsets[k] = rs.blob_range_off[k];
 				}
 			}
 			out[request] = st;
@@ -831,16 +975,15 @@ namespace aclb200
 				return;
 			const int k = int(p.debug_which);
 			const uint32_t total = rs.num_animated[0] + rs.num_animated[1] + rs.num_animated[2];
-			for (uint32_t j = threadIdx.x; j < total && j < p.debug_max_sub_tracks; j += blockDim.x)
+			for (uint32_t slot = threadIdx.x; slot < total && slot < p.debug_max_sub_tracks; slot += blockDim.x)
 			{
-				uint32_t kind = 0, rank = j;
-				if (rank >= rs.num_animated[0]) { rank -= rs.num_animated[0]; kind = 1; }
-				if (kind == 1 && rank >= rs.num_animated[1]) { rank -= rs.num_animated[1]; kind = 2; }
+				const Entry e = load_entry(rs, k, slot);
+				const bool four = slot < rs.num_animated[0] && (rs.clip_flags & k_clip_rot_full);
 				uint32_t xi, yi, zi, wi;
-				const uint32_t code = unpack_sample_ints(rs, k, kind, rank, j, xi, yi, zi, wi);
-				uint32_t* dst = out + (size_t(request) * p.debug_max_sub_tracks + j) * 4;
+				unpack_sample_ints<false>(rs, nullptr, k, e, four, xi, yi, zi, wi);
+				uint32_t* dst = out + (size_t(request) * p.debug_max_sub_tracks + slot) * 4;
 				dst[0] = xi; dst[1] = yi; dst[2] = zi;
-				dst[3] = code;
+				dst[3] = e.offset_code & 0xFFu;
 			}
 		}
 
@@ -849,7 +992,7 @@ namespace aclb200
 		// ---------------------------------------------------------------------------------------------------
 		struct ScalarReqState
 		{
-			const uint8_t* blob;
+			const uint8_t* image;
 			const ScalarTrackDesc* tracks;
 			uint8_t* out;
 			float    alpha;
@@ -857,7 +1000,7 @@ namespace aclb200
 			uint32_t kf_bit[2];
 			uint32_t constant_off;
 			uint32_t range_off;
-			uint32_t animated_off;
+			uint32_t stream_off;
 		};
 
 		__device__ void seek_scalar(const DecodeParams& p, uint32_t request_index, ScalarReqState& rs)
@@ -881,69 +1024,65 @@ namespace aclb200
 			float alpha;
 			find_key_frames(clip.num_samples, clip.sample_rate, sample_time, p.rounding_policy, looping_policy, key_frame0, key_frame1, alpha);
 
-			rs.blob = p.blobs + clip.blob_offset;
-			rs.tracks = reinterpret_cast<const ScalarTrackDesc*>(p.index + clip.index_offset + clip.bone_table_offset);
+			rs.image = p.data + clip.data_offset;
+			rs.tracks = reinterpret_cast<const ScalarTrackDesc*>(rs.image + clip.bone_table_offset);
 			rs.alpha = alpha;
 			rs.num_tracks = clip.num_tracks;
-			rs.kf_bit[0] = key_frame0 * clip.num_constant[0];		// num_bits_per_frame, decompression.scalar.h:208-209
-			rs.kf_bit[1] = key_frame1 * clip.num_constant[0];
-			rs.constant_off = clip.constant_offset[0];
-			rs.range_off = clip.constant_offset[1];
-			rs.animated_off = clip.constant_offset[2];
+			rs.kf_bit[0] = key_frame0 * clip.num_animated_total;		// num_bits_per_frame, decompression.scalar.h:208-209
+			rs.kf_bit[1] = key_frame1 * clip.num_animated_total;
+			rs.constant_off = clip.const_rot_offset;
+			rs.range_off = clip.const_vec_offset;
+			rs.stream_off = clip.seg_table_offset;
 		}
 
-		// The animated values of scalar clips start at an arbitrary byte: read through the enclosing aligned words.
-		__device__ __forceinline__ uint32_t read_bits32_unaligned(const uint8_t* base, uint32_t bit_offset)
+		__device__ __forceinline__ uint32_t read_stream32(const uint32_t* words, uint32_t bit)
 		{
-			const uintptr_t address = reinterpret_cast<uintptr_t>(base) + (bit_offset >> 3);
-			const uint32_t* words = reinterpret_cast<const uint32_t*>(address & ~uintptr_t(3));
-			const uint32_t shift = uint32_t(address & 3) * 8 + (bit_offset & 7);		// 0..31
-			const uint32_t w0 = __byte_perm(__ldg(words + 0), 0, 0x0123);
-			const uint32_t w1 = __byte_perm(__ldg(words + 1), 0, 0x0123);
-			return __funnelshift_l(w1, w0, shift);
+			const uint32_t hi = __ldg(words + (bit >> 5));
+			const uint32_t lo = __ldg(words + (bit >> 5) + 1);
+			return __funnelshift_l(lo, hi, bit & 31);
 		}
 
 		template<int COMPONENTS, bool PER_TRACK>
 		__device__ __forceinline__ void decode_scalar_track(const DecodeParams& p, const ScalarReqState& rs, uint32_t track, float* out)
 		{
-			const ScalarTrackDesc desc = rs.tracks[track];
-			const uint32_t num_bits = desc.value_index_and_bits & 0xFFu;
-			const uint32_t value_index = desc.value_index_and_bits >> 8;
+			const uint4 raw = __ldg(reinterpret_cast<const uint4*>(rs.tracks) + track);
+			const uint32_t num_bits = raw.y & 0xFFu;
+			const uint32_t value_index = raw.y >> 8;
+			const float inv_max = __uint_as_float(raw.z);
 			float alpha = rs.alpha;
 			if (PER_TRACK)
 				alpha = apply_rounding_policy(rs.alpha, track_rounding_policy(p, track));	// decompression.scalar.h:235-247,273-280
 
 			if (num_bits == 0)
 			{
-				const float* constants = reinterpret_cast<const float*>(rs.blob + rs.constant_off) + value_index;
+				const float* constants = reinterpret_cast<const float*>(rs.image + rs.constant_off) + value_index;
 #pragma unroll
 				for (int c = 0; c < COMPONENTS; ++c)
 					out[c] = __ldg(constants + c);
 				return;
 			}
 
-			const uint8_t* animated = rs.blob + rs.animated_off;
-			const uint32_t bit0 = rs.kf_bit[0] + desc.bit_offset;
-			const uint32_t bit1 = rs.kf_bit[1] + desc.bit_offset;
+			const uint32_t* words = reinterpret_cast<const uint32_t*>(rs.image + rs.stream_off);
+			const uint32_t bit0 = rs.kf_bit[0] + raw.x;
+			const uint32_t bit1 = rs.kf_bit[1] + raw.x;
 			if (num_bits == 32)
 			{
 #pragma unroll
 				for (int c = 0; c < COMPONENTS; ++c)
 				{
-					const float v0 = __uint_as_float(read_bits32_unaligned(animated, bit0 + 32 * c));
-					const float v1 = __uint_as_float(read_bits32_unaligned(animated, bit1 + 32 * c));
+					const float v0 = __uint_as_float(read_stream32(words, bit0 + 32 * c));
+					const float v1 = __uint_as_float(read_stream32(words, bit1 + 32 * c));
 					out[c] = lerp(v0, v1, alpha);
 				}
 				return;
 			}
 
-			const float inv_max = inv_max_value(num_bits);
-			const float* range = reinterpret_cast<const float*>(rs.blob + rs.range_off) + value_index;
+			const float* range = reinterpret_cast<const float*>(rs.image + rs.range_off) + value_index;
 #pragma unroll
 			for (int c = 0; c < COMPONENTS; ++c)
 			{
-				const uint32_t i0 = read_bits32_unaligned(animated, bit0 + num_bits * c) >> (32 - num_bits);
-				const uint32_t i1 = read_bits32_unaligned(animated, bit1 + num_bits * c) >> (32 - num_bits);
+				const uint32_t i0 = read_stream32(words, bit0 + num_bits * c) >> (32 - num_bits);
+				const uint32_t i1 = read_stream32(words, bit1 + num_bits * c) >> (32 - num_bits);
 				const float range_min = __ldg(range + c);
 				const float range_extent = __ldg(range + COMPONENTS + c);
 				const float v0 = fmuladd(fmul(u2f(i0), inv_max), range_extent, range_min);
@@ -972,7 +1111,7 @@ namespace aclb200
 			const uint32_t num_slots = num_requests * p.max_tracks;
 			for (uint32_t slot = threadIdx.x; slot < num_slots; slot += k_threads_per_block)
 			{
-				const uint32_t local_request = p.max_tracks_magic != 0 ? __umulhi(slot, p.max_tracks_magic) : slot;
+				const uint32_t local_request = fast_div(slot, p.magic_tracks);
 				const uint32_t track = slot - local_request * p.max_tracks;
 				const ScalarReqState& rs = s_req[local_request];
 				if (track >= rs.num_tracks)
@@ -1006,61 +1145,109 @@ namespace aclb200
 				dst[c] = value[c];
 		}
 
-		template<template<int, bool> class Launcher>
-		cudaError_t dispatch_transform(const DecodeParams& params, cudaStream_t stream)
+		uint32_t division_magic(uint32_t divisor)
 		{
-			const bool per_track = params.per_track_rounding != 0;
-			switch (params.normalization)
-			{
-			case ACLB200_NORMALIZE_NEVER: return per_track ? Launcher<0, true>::launch(params, stream) : Launcher<0, false>::launch(params, stream);
-			case ACLB200_NORMALIZE_LERP_ONLY: return per_track ? Launcher<1, true>::launch(params, stream) : Launcher<1, false>::launch(params, stream);
-			default: return per_track ? Launcher<2, true>::launch(params, stream) : Launcher<2, false>::launch(params, stream);
-			}
+			// floor(v / d) == mulhi(v, magic) for v < 2^32 / d, which every slot index here satisfies (v < 2^18 + 2048 items, d <= 2^18)
+			return divisor <= 1 ? 0u : uint32_t((uint64_t(1) << 32) / divisor) + 1u;
 		}
 
 		template<int NORM, bool PER_TRACK>
-		struct TracksLauncher
+		cudaError_t launch_tracks(const DecodeParams& params, cudaStream_t stream)
 		{
-			static cudaError_t launch(const DecodeParams& params, cudaStream_t stream)
-			{
-				const uint32_t blocks = (params.num_requests + params.requests_per_block - 1) / params.requests_per_block;
-				transform_decompress_tracks_kernel<NORM, PER_TRACK><<<blocks, k_threads_per_block, 0, stream>>>(params);
-				return cudaGetLastError();
-			}
-		};
+			const uint32_t blocks = (params.num_requests + params.requests_per_block - 1) / params.requests_per_block;
+			if (params.stage_bytes != 0)
+				transform_decompress_tracks_kernel<NORM, PER_TRACK, true><<<blocks, k_threads_per_block, params.smem_bytes, stream>>>(params);
+			else
+				transform_decompress_tracks_kernel<NORM, PER_TRACK, false><<<blocks, k_threads_per_block, 0, stream>>>(params);
+			return cudaGetLastError();
+		}
 
 		template<int NORM, bool PER_TRACK>
-		struct TrackLauncher
+		cudaError_t launch_track(const DecodeParams& params, cudaStream_t stream)
 		{
-			static cudaError_t launch(const DecodeParams& params, cudaStream_t stream)
-			{
-				const uint32_t blocks = (params.num_requests + 127) / 128;
-				transform_decompress_track_kernel<NORM, PER_TRACK><<<blocks, 128, 0, stream>>>(params);
-				return cudaGetLastError();
-			}
-		};
+			const uint32_t blocks = (params.num_requests + 127) / 128;
+			transform_decompress_track_kernel<NORM, PER_TRACK><<<blocks, 128, 0, stream>>>(params);
+			return cudaGetLastError();
+		}
+
+		template<int NORM, bool PER_TRACK>
+		cudaError_t set_smem_attribute(int optin_limit, int& min_available)
+		{
+			// the opt-in limit covers static + dynamic shared memory
+			cudaFuncAttributes attributes;
+			cudaError_t error = cudaFuncGetAttributes(&attributes, transform_decompress_tracks_kernel<NORM, PER_TRACK, true>);
+			if (error != cudaSuccess)
+				return error;
+			const int available = optin_limit - int(attributes.sharedSizeBytes);
+			if (available < min_available)
+				min_available = available;
+			return cudaFuncSetAttribute(transform_decompress_tracks_kernel<NORM, PER_TRACK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, available);
+		}
 	}
 
-	// requests_per_block and the division magic for a launch over `max_tracks` wide poses
-	void plan_launch(DecodeParams& params)
+	// Called once per context: lets the staged kernels use large dynamic shared memory windows. `max_dynamic_smem` comes in as the
+	// device's opt-in limit and goes out as what a launch may actually request.
+	cudaError_t configure_kernels(int& max_dynamic_smem)
+	{
+		const int optin_limit = max_dynamic_smem - 1024;
+		int available = optin_limit;
+		cudaError_t error = set_smem_attribute<0, false>(optin_limit, available);
+		if (error == cudaSuccess) error = set_smem_attribute<0, true>(optin_limit, available);
+		if (error == cudaSuccess) error = set_smem_attribute<1, false>(optin_limit, available);
+		if (error == cudaSuccess) error = set_smem_attribute<1, true>(optin_limit, available);
+		if (error == cudaSuccess) error = set_smem_attribute<2, false>(optin_limit, available);
+		if (error == cudaSuccess) error = set_smem_attribute<2, true>(optin_limit, available);
+		max_dynamic_smem = available;
+		return error;
+	}
+
+	// requests_per_block, the division magics and the shared memory staging of a launch
+	void plan_launch(DecodeParams& params, uint32_t max_key_frame_bytes, int max_dynamic_smem)
 	{
 		const uint32_t max_tracks = params.max_tracks == 0 ? 1 : params.max_tracks;
-		uint32_t requests_per_block = k_target_poses_per_block / max_tracks;
+		uint32_t requests_per_block = k_target_items_per_block / max_tracks;
 		if (requests_per_block < 1) requests_per_block = 1;
 		if (requests_per_block > k_max_requests_per_block) requests_per_block = k_max_requests_per_block;
+
+		// bytes per staged key frame: up to 15 bytes of alignment skew + the key frame + one extra word for the funnel shift
+		uint32_t stage_bytes = (max_key_frame_bytes + 48 + 15) & ~15u;
+		if (max_key_frame_bytes == 0)
+			stage_bytes = 0;
+		// keep several blocks resident per SM: at most ~40 KB of staging per block, else fewer requests per block
+		const uint32_t staging_budget = 40u * 1024u;
+		while (stage_bytes != 0 && requests_per_block > 1 && requests_per_block * 2 * stage_bytes > staging_budget)
+			requests_per_block = (requests_per_block + 1) / 2;
+		if (stage_bytes != 0 && uint64_t(requests_per_block) * 2 * stage_bytes > uint64_t(max_dynamic_smem > 4096 ? max_dynamic_smem - 4096 : 0))
+			stage_bytes = 0;		// a single key frame pair does not fit: read the streams from global memory instead
+
 		params.requests_per_block = requests_per_block;
-		// floor(slot / max_tracks) == mulhi(slot, magic) for slot < 2^16 * ... (slot < requests_per_block * max_tracks <= 2^18 + 2048)
-		params.max_tracks_magic = max_tracks == 1 ? 0u : uint32_t((uint64_t(1) << 32) / max_tracks) + 1u;
+		params.stage_bytes = stage_bytes;
+		params.smem_bytes = requests_per_block * 2 * stage_bytes;
+		params.magic_tracks = division_magic(max_tracks);
+		params.magic_rot = division_magic(params.max_animated[0]);
+		params.magic_vec = division_magic(params.max_animated[1] + params.max_animated[2]);
 	}
 
 	cudaError_t launch_transform_decompress_tracks(const DecodeParams& params, uint32_t /*math_mode*/, cudaStream_t stream)
 	{
-		return dispatch_transform<TracksLauncher>(params, stream);
+		const bool per_track = params.per_track_rounding != 0;
+		switch (params.normalization)
+		{
+		case ACLB200_NORMALIZE_NEVER: return per_track ? launch_tracks<0, true>(params, stream) : launch_tracks<0, false>(params, stream);
+		case ACLB200_NORMALIZE_LERP_ONLY: return per_track ? launch_tracks<1, true>(params, stream) : launch_tracks<1, false>(params, stream);
+		default: return per_track ? launch_tracks<2, true>(params, stream) : launch_tracks<2, false>(params, stream);
+		}
 	}
 
 	cudaError_t launch_transform_decompress_track(const DecodeParams& params, uint32_t /*math_mode*/, cudaStream_t stream)
 	{
-		return dispatch_transform<TrackLauncher>(params, stream);
+		const bool per_track = params.per_track_rounding != 0;
+		switch (params.normalization)
+		{
+		case ACLB200_NORMALIZE_NEVER: return per_track ? launch_track<0, true>(params, stream) : launch_track<0, false>(params, stream);
+		case ACLB200_NORMALIZE_LERP_ONLY: return per_track ? launch_track<1, true>(params, stream) : launch_track<1, false>(params, stream);
+		default: return per_track ? launch_track<2, true>(params, stream) : launch_track<2, false>(params, stream);
+		}
 	}
 
 	cudaError_t launch_transform_debug_seek(const DecodeParams& params, aclb200_seek_state* d_out, cudaStream_t stream)

@@ -1,37 +1,45 @@
-// acl_b200/csrc/layout.h -- what lives in HBM for a clip set, shared by the host builder and the kernels.
+// acl_b200/csrc/layout.h -- what lives in HBM for a clip set, shared by the host builder (clipset.cpp) and the kernels.
 //
-// A clip set is three device buffers:
-//   blobs : the caller's compressed_tracks buffers, byte for byte, each starting on a 16 byte boundary
-//           (the format's own alignment, includes/acl/core/compressed_tracks.h:53) plus 64 bytes of tail
-//           slack so the big-endian unaligned reads the format relies on never leave the allocation.
-//   clips : one ClipDesc per clip: everything decompression_context::initialize() caches
-//           (initialize_v0, decompression/impl/decompression.transform.h:84-132) plus offsets the reference
-//           re-derives on every seek (transform_tracks_header::get_segment_data, core/impl/compressed_headers.h:310-324).
-//   index : per clip acceleration tables that replace the two serial scans of the CPU decoder:
-//           - BoneDesc[num_tracks]   : rank of every bone among the constant / animated sub-tracks of its kind
-//                                      (the popcount walk of decompress_track_v0, decompression.transform.h:1873-1891)
-//           - SegDesc[num_segments]  : per segment offsets
-//           - u32 entries[segment][animated sub-track] : bit offset inside a key frame + bit width, i.e. the
-//                                      running sum kept in animated_track_data_bit_offset
-//                                      (animated_track_cache.transform.h:598-599,653)
-//           The index costs ~6 % of the blob bytes and makes every (request, bone) independent.
+// At upload every compressed_tracks blob is TRANSCODED once into a GPU-native "clip image"; the original bytes are not
+// kept on the device. The compressed payload itself (the variable bit rate key frame streams) is carried over bit for
+// bit -- only the byte order inside each 32-bit word is normalised so a little-endian machine can read the big-endian
+// stream with aligned word loads -- while the metadata the CPU decoder walks with serial cursors is re-laid out so that
+// every (request, sub-track) is independent work and needs one or two 16-byte loads:
+//
+//   clips : ClipDesc[num_clips]                   what decompression_context::initialize() caches (initialize_v0,
+//                                                 includes/acl/decompression/impl/decompression.transform.h:84-132)
+//   data  : per clip, 16-byte aligned sections
+//     BoneDesc[num_tracks]            u64   (type, rank) of the rotation / translation / scale sub-track of each bone: the
+//                                           prefix popcounts of decompress_track_v0 (decompression.transform.h:1873-1891)
+//     ConstRot[num_constant_rot][2]   f32x4 constant rotations with W already reconstructed (quat_from_positive_w4,
+//                                           math/quatf.h:135-147), [1] = also normalised (policy `always`); same IEEE ops on the host
+//     ConstVec[num_constant_trans + num_constant_scale] f32x4 constant translations then scales
+//     AnimDesc[num_animated_total]    48 B  clip range of each animated sub-track (remap_clip_range_data4 /
+//                                           unpack_animated_vector3, animated_track_cache.transform.h:391-466,947-958) + the bone
+//                                           it belongs to (the "select" the CPU does by walking the 2-bit type arrays)
+//     start_indices[num_segments + 1] u32   segment_start_indices + sentinel (only when num_segments > 1)
+//     SegDesc[num_segments]           32 B
+//     Entry[num_segments][num_animated_total] 16 B  per segment and sub-track: bit offset inside a key frame (the running sum of
+//                                           animated_track_data_bit_offset, animated_track_cache.transform.h:598-599,653), bit
+//                                           width, the 6 segment range bytes (or the constant sample when the bit rate is 0)
+//                                           and 1 / (2^bits - 1)
+//     stream[num_segments]            u32[] key frames of the segment, byte-swapped words, 16-byte aligned, 64 B zero tail
 #pragma once
 
 #include <stdint.h>
 
 namespace aclb200
 {
-	// ---- reference binary format constants (core/impl/compressed_headers.h) -------------------------------
+	// ---- reference binary format constants (includes/acl/core/impl/compressed_headers.h) ----------------
 	constexpr uint32_t k_tag = 0xac11ac11u;						// core/buffer_tag.h:49
 	constexpr uint32_t k_version_first = 7;						// v02_00_00, core/compressed_tracks_version.h:75
 	constexpr uint32_t k_version_raw31 = 9;						// v02_01_99_1: raw bit rate stored as 31 in the per-track format
 	constexpr uint32_t k_version_latest = 10;					// v02_01_00
 	constexpr uint32_t k_track_qvvf = 12;						// core/track_types.h:68
-	constexpr uint32_t k_tracks_header_offset = 8;				// after raw_buffer_header {size, hash}
 	constexpr uint32_t k_type_header_offset = 32;				// transform_tracks_header / scalar_tracks_header
 	constexpr uint32_t k_transform_header_size = 52;
-	constexpr uint32_t k_blob_alignment = 16;
-	constexpr uint32_t k_tail_slack = 64;
+	constexpr uint32_t k_section_alignment = 16;
+	constexpr uint32_t k_stream_tail = 64;						// zero bytes after every stream (the reference pads 15, compress.transform.impl.h:395-396)
 
 	constexpr uint32_t k_rot_full = 0;							// rotation_format8, core/track_formats.h:48-53
 	constexpr uint32_t k_rot_drop_w_full = 2;
@@ -50,8 +58,7 @@ namespace aclb200
 
 	struct alignas(16) ClipDesc
 	{
-		uint64_t blob_offset;				// byte offset of the clip inside the blobs buffer
-		uint64_t index_offset;				// byte offset of the clip's tables inside the index buffer
+		uint64_t data_offset;				// byte offset of the clip image inside the data buffer
 		uint32_t num_tracks;
 		uint32_t num_samples;
 		float    sample_rate;
@@ -62,16 +69,18 @@ namespace aclb200
 		float    duration_wrap;				// get_finite_duration(wrap)
 		uint32_t num_animated[3];			// rotation, translation, scale
 		uint32_t num_constant[3];
-		uint32_t constant_offset[3];		// blob relative: constant rotations / translations / scales
-		uint32_t clip_range_offset[3];		// blob relative: clip range of animated rotations / translations / scales
-		uint32_t bone_table_offset;			// index relative: BoneDesc[num_tracks]
-		uint32_t seg_table_offset;			// index relative: SegDesc[num_segments]
-		uint32_t start_indices_offset;		// blob relative: segment_start_indices (only when num_segments > 1)
-		uint32_t num_animated_total;		// rotations + translations + scales (entries per segment)
-		// scalar clips (decompression.scalar.h) reuse: num_constant[0] = num_bits_per_frame,
-		// constant_offset[0..2] = constant values / range values / animated values, bone_table_offset = ScalarTrackDesc[]
-		uint32_t hash;
-		uint32_t size;
+		// image relative byte offsets
+		uint32_t bone_table_offset;			// BoneDesc[num_tracks]            (scalar clips: ScalarTrackDesc[num_tracks])
+		uint32_t const_rot_offset;			// float4[num_constant[0]][2]      (scalar clips: constant values)
+		uint32_t const_vec_offset;			// float4[num_constant[1] + [2]]   (scalar clips: range values)
+		uint32_t anim_table_offset;			// AnimDesc[num_animated_total]
+		uint32_t start_indices_offset;		// u32[num_segments + 1]
+		uint32_t seg_table_offset;			// SegDesc[num_segments]           (scalar clips: offset of the single stream)
+		uint32_t num_animated_total;		// (scalar clips: num_bits_per_frame)
+		uint32_t image_size;
+		uint32_t hash;						// compressed_tracks::get_hash()
+		uint32_t size;						// compressed_tracks::get_size()
+		uint32_t pad[2];
 	};
 	static_assert(sizeof(ClipDesc) % 16 == 0, "ClipDesc must stay 16 byte sized");
 
@@ -80,29 +89,52 @@ namespace aclb200
 	//   index = (desc >> (22 * k + 2)) & 0xFFFFF rank among the constant or animated sub-tracks of that kind
 	constexpr uint32_t k_bone_kind_shift = 22;
 	constexpr uint32_t k_bone_index_mask = 0xFFFFFu;
-	constexpr uint32_t k_max_tracks = 1u << 18;					// scale rank has 18 bits left
+	constexpr uint32_t k_max_tracks = 1u << 18;					// the scale rank has 18 bits left
+
+	// Clip-level data of one animated sub-track: two 16 byte loads give the clip range and the destination bone.
+	struct alignas(16) AnimDesc
+	{
+		float    extent[3];		// clip range extent xyz (1.0 when the format carries no clip range)
+		uint32_t bone;			// track index this sub-track writes to
+		float    min[3];		// clip range min xyz (0.0 when the format carries no clip range)
+		uint32_t pad;
+	};
+	static_assert(sizeof(AnimDesc) == 32, "AnimDesc is 32 bytes");
 
 	struct alignas(16) SegDesc
 	{
-		uint32_t animated_offset;			// blob relative byte offset of the segment's animated bit stream
+		uint32_t stream_offset;				// image relative, 16 byte aligned: byte-swapped 32-bit words of the segment's key frames
 		uint32_t pose_bit_size;				// segment_header::animated_pose_bit_size
 		uint32_t sample_indices;			// stripped_segment_header_t::sample_indices (0xFFFFFFFF when nothing is stripped)
-		uint32_t entries_offset;			// index relative: u32 entries[num_animated_total]
-		uint32_t range_offset[3];			// blob relative: segment range data of rotations (SOA groups of 4) / translations / scales (AOS 6 B)
-		uint32_t format_offset;				// blob relative: format_per_track_data (kept for the parity hooks)
+		uint32_t entries_offset;			// image relative: Entry[num_animated_total]
+		// offsets inside the ORIGINAL blob, reported by the seek parity hook (persistent_transform_decompression_context_v0)
+		uint32_t blob_format_offset;
+		uint32_t blob_range_offset;
+		uint32_t blob_animated_offset;
+		uint32_t stream_bytes;				// bytes of key frame data stored (without the tail)
 	};
 	static_assert(sizeof(SegDesc) == 32, "SegDesc is 32 bytes");
 
-	// Sub-track entry: (bit offset inside the key frame << 8) | code, code = number of bits per component in the
-	// stream (1..23), 0 = constant inside the segment (sample lives in the segment range bytes), 32 | k_entry_raw = raw floats.
+	// Entry::offset_code = (bit offset inside the key frame << 8) | code
+	//   code 1..23           bits per component, quantised, segment + clip range apply
+	//   code 0               constant inside the segment: range_lo/range_hi hold the 3 x 16 bit sample, only the clip range applies
+	//   code 32 | k_entry_raw  raw 32-bit floats (3 components, 4 for quatf_full rotations), no range applies
 	constexpr uint32_t k_entry_raw = 0x80u;
-	constexpr uint32_t k_entry_bits_mask = 0x3Fu;
-
-	// ScalarTrackDesc: { bit offset inside a frame, (value index << 8) | num_bits } ; value index counts floats in
-	// constant_values (num_bits == 0) or range_values (0 < num_bits < 32).
-	struct ScalarTrackDesc
+	struct alignas(16) Entry
 	{
-		uint32_t bit_offset;
-		uint32_t value_index_and_bits;
+		uint32_t offset_code;
+		uint32_t range_lo;		// code 1..23: min.x | min.y << 8 | min.z << 16 | extent.x << 24      code 0: x | y << 16
+		uint32_t range_hi;		// code 1..23: extent.y | extent.z << 8                               code 0: z
+		float    inv_max;		// 1 / (2^code - 1) (PackedTableEntry::max_value, math/vector4_packing.h:927-929); 1 / 65535 for code 0
+	};
+	static_assert(sizeof(Entry) == 16, "Entry is 16 bytes");
+
+	// Scalar clips (decompression/impl/decompression.scalar.h): one descriptor per track.
+	struct alignas(16) ScalarTrackDesc
+	{
+		uint32_t bit_offset;			// inside a frame
+		uint32_t value_index_and_bits;	// (index of the first float in constant / range values << 8) | num_bits (0 constant, 32 raw)
+		float    inv_max;
+		uint32_t pad;
 	};
 }
