@@ -57,8 +57,12 @@ namespace aclb200
 			params.pose_stride = options->pose_stride_bytes != 0 ? options->pose_stride_bytes : uint64_t(params.max_tracks) * params.bone_stride;
 			if (!single_track && params.pose_stride < uint64_t(params.max_tracks) * params.bone_stride)
 				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "pose_stride_bytes is smaller than one pose");
-			if (is_transform && (params.pose_stride % (options->output_layout == ACLB200_LAYOUT_QVV48 ? 16 : 8)) != 0)
-				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "pose_stride_bytes must keep bones 16 (QVV48) / 8 (QVV40) byte aligned");
+			if (is_transform)
+			{
+				const uint64_t alignment = options->output_layout == ACLB200_LAYOUT_QVV48 ? 16 : 8;
+				if ((params.pose_stride % alignment) != 0 || (reinterpret_cast<uintptr_t>(d_out) % alignment) != 0)
+					return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "the output pointer and pose_stride_bytes must keep bones 16 (QVV48) / 8 (QVV40) byte aligned");
+			}
 			params.rounding_policy = options->rounding_policy;
 			params.looping_policy = options->looping_policy;
 			params.normalization = options->normalization;
@@ -73,7 +77,12 @@ namespace aclb200
 			params.variable_defaults = options->d_variable_defaults;
 			params.per_track_policies = options->d_per_track_rounding;
 			params.layout = options->output_layout;
-			plan_launch(params, is_transform && !single_track ? clipset->max_key_frame_bytes : 0u, context->max_dynamic_smem);
+			// `skipped` default sub-tracks must keep what the caller's buffer holds: those launches store sub-tracks straight to
+			// global memory instead of assembling whole poses in shared memory
+			const bool any_skipped = options->default_rotation_mode == ACLB200_DEFAULT_SKIPPED || options->default_translation_mode == ACLB200_DEFAULT_SKIPPED
+				|| options->default_scale_mode == ACLB200_DEFAULT_SKIPPED;
+			const bool tracks_launch = is_transform && !single_track;
+			plan_launch(params, tracks_launch ? clipset->max_key_frame_bytes : 0u, context->max_dynamic_smem, tracks_launch && !any_skipped);
 			return ACLB200_OK;
 		}
 
@@ -241,6 +250,21 @@ extern "C"
 		if (status != ACLB200_OK || num_requests == 0)
 			return status;
 		cudaSetDevice(context->device);
+
+		// Main path: the persistent TMA pipeline (pipeline.cu). It assembles whole poses in shared memory, so launches that must
+		// leave `skipped` default sub-tracks untouched, or whose poses do not fit in shared memory, use the plain kernels instead.
+		const bool any_skipped = options->default_rotation_mode == ACLB200_DEFAULT_SKIPPED || options->default_translation_mode == ACLB200_DEFAULT_SKIPPED
+			|| options->default_scale_mode == ACLB200_DEFAULT_SKIPPED;
+		if (!any_skipped && clipset->max_key_frame_bytes != 0)
+		{
+			DecodeParams pipeline_params = params;
+			if (plan_pipeline(pipeline_params, clipset->max_key_frame_bytes, context->max_dynamic_smem, context->num_sms))
+			{
+				const bool rows_16 = options->output_layout == ACLB200_LAYOUT_QVV48 || clipset->all_tracks_even;
+				pipeline_params.out_bulk = rows_16 && ((uint64_t(reinterpret_cast<uintptr_t>(d_out)) | pipeline_params.pose_stride) & 15) == 0 ? 1u : 0u;
+				return finish_launch(context, launch_transform_pipeline(pipeline_params, static_cast<cudaStream_t>(stream)), "decompress_tracks (pipeline)");
+			}
+		}
 		return finish_launch(context, launch_transform_decompress_tracks(params, options->math_mode, static_cast<cudaStream_t>(stream)), "decompress_tracks");
 	}
 

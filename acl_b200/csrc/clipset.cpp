@@ -632,6 +632,8 @@ namespace aclb200
 			blob_bytes += desc.size;
 			set->host_looping[clip] = parsed.looping_policy;
 			max_tracks = desc.num_tracks > max_tracks ? desc.num_tracks : max_tracks;
+			if (desc.num_tracks % 2 != 0)
+				set->all_tracks_even = false;
 			min_tracks = desc.num_tracks < min_tracks ? desc.num_tracks : min_tracks;
 			if (parsed.track_type == k_track_qvvf)
 			{

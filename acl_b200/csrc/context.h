@@ -35,6 +35,7 @@ struct aclb200_clipset
 	uint32_t max_animated[3] = { 0, 0, 0 };			// largest number of animated rotation / translation / scale sub-tracks of a clip
 	uint32_t max_animated_total = 0;
 	uint32_t max_key_frame_bytes = 0;				// largest ceil(animated_pose_bit_size / 8) of any segment
+	bool all_tracks_even = true;					// every clip has an even number of tracks (40 byte bones then give 16 byte granular rows)
 
 	uint8_t* d_data = nullptr;
 	aclb200::ClipDesc* d_clips = nullptr;
@@ -60,8 +61,15 @@ namespace aclb200
 		uint32_t magic_tracks;				// floor(2^32 / d) + 1 for d = max_tracks / max_animated[0] / max(max_animated[1] + [2]):
 		uint32_t magic_rot;					// turns slot / d into a mulhi (0 when d == 1)
 		uint32_t magic_vec;
+		uint32_t magic_chunks;
 		uint32_t stage_bytes;				// shared memory bytes reserved per staged key frame (0 = read the streams from global memory)
+		uint32_t smem_pose_bytes;			// shared memory bytes reserved per assembled pose (0 = phases store straight to global memory)
+		uint32_t smem_stage_offset;			// carve-up of the dynamic shared memory: ReqState[] | key frame windows | poses
+		uint32_t smem_out_offset;
 		uint32_t smem_bytes;				// dynamic shared memory of the launch
+		uint32_t out_vector16;				// poses can leave shared memory with 16 byte stores
+		uint32_t out_bulk;					// pipeline: every pose row is 16 byte granular, rows leave shared memory as TMA bulk stores
+		uint32_t grid_blocks;				// pipeline: persistent grid size
 		uint8_t* out;
 		uint64_t pose_stride;
 		uint32_t bone_stride;				// 48 or 40 (transform), components * 4 (scalar)
@@ -83,7 +91,7 @@ namespace aclb200
 	};
 
 	// kernels.cu
-	void plan_launch(DecodeParams& params, uint32_t max_key_frame_bytes, int max_dynamic_smem);
+	void plan_launch(DecodeParams& params, uint32_t max_key_frame_bytes, int max_dynamic_smem, bool allow_output_staging);
 	cudaError_t launch_transform_decompress_tracks(const DecodeParams& params, uint32_t math_mode, cudaStream_t stream);
 	cudaError_t launch_transform_decompress_track(const DecodeParams& params, uint32_t math_mode, cudaStream_t stream);
 	cudaError_t launch_transform_debug_seek(const DecodeParams& params, aclb200_seek_state* d_out, cudaStream_t stream);
@@ -91,4 +99,8 @@ namespace aclb200
 	cudaError_t launch_scalar_decompress_tracks(const DecodeParams& params, cudaStream_t stream);
 	cudaError_t launch_scalar_decompress_track(const DecodeParams& params, cudaStream_t stream);
 	cudaError_t configure_kernels(int& max_dynamic_smem);
+	// pipeline.cu
+	cudaError_t configure_pipeline_kernels(int optin_limit, int& min_available);
+	bool plan_pipeline(DecodeParams& params, uint32_t max_key_frame_bytes, int max_dynamic_smem, int num_sms);
+	cudaError_t launch_transform_pipeline(const DecodeParams& params, cudaStream_t stream);
 }
