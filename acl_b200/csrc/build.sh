@@ -3,7 +3,7 @@
 # Used by __graft_entry__.build(); nvcc cross-compiles without a GPU.
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
-OUT="$HERE/../libaclb200.so"
+OUT="${ACLB200_OUT:-$HERE/../libaclb200.so}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "$NVCC" -std=c++17 -O3 -lineinfo \
   -gencode arch=compute_100a,code=sm_100a \

@@ -70,6 +70,8 @@ namespace aclb200
 		uint32_t out_vector16;				// poses can leave shared memory with 16 byte stores
 		uint32_t out_bulk;					// pipeline: every pose row is 16 byte granular, rows leave shared memory as TMA bulk stores
 		uint32_t grid_blocks;				// pipeline: persistent grid size
+		uint32_t smem_stage_size;			// pipeline: bytes of one stage (key frame windows + poses)
+		float    one;						// 1.0f the compiler cannot see (keeps f32x2 mul + add unfused, see pipeline.cu)
 		uint8_t* out;
 		uint64_t pose_stride;
 		uint32_t bone_stride;				// 48 or 40 (transform), components * 4 (scalar)
