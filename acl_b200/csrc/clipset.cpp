@@ -488,6 +488,7 @@ namespace aclb200
 						Entry entry = {};
 						uint32_t code, stream_bits;
 						entry.inv_max = 1.0F;
+						entry.extent[0] = entry.extent[1] = entry.extent[2] = 1.0F;
 						if (variable[kind])
 						{
 							const uint32_t stored = format[kind_format_offset[kind] + index];
@@ -525,8 +526,8 @@ namespace aclb200
 								}
 								code = 0;
 								stream_bits = 0;
-								entry.range_lo = x | (y << 16);
-								entry.range_hi = z;
+								const uint32_t sample[3] = { x, y, z };
+								std::memcpy(entry.min, sample, sizeof(sample));
 								entry.inv_max = 1.0F / 65535.0F;
 							}
 							else if (stored == raw_marker)
@@ -538,8 +539,13 @@ namespace aclb200
 							{
 								code = stored;
 								stream_bits = stored * 3;
-								entry.range_lo = uint32_t(r[0]) | (uint32_t(r[1]) << 8) | (uint32_t(r[2]) << 16) | (uint32_t(r[3]) << 24);
-								entry.range_hi = uint32_t(r[4]) | (uint32_t(r[5]) << 8);
+								// unpack_segment_range_data: u8 -> float, times 1 / 255 in float (:157-298; vectors math/vector4_packing.h:781-818)
+								const float n = 1.0F / 255.0F;
+								for (int c = 0; c < 3; ++c)
+								{
+									entry.min[c] = float(r[c]) * n;
+									entry.extent[c] = float(r[3 + c]) * n;
+								}
 								entry.inv_max = inv_max_value(stored);
 							}
 							else

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <stdint.h>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -26,6 +27,27 @@ struct aclb200_context
 	cudaStream_t host_stream = nullptr;
 };
 
+namespace aclb200
+{
+	// What a clip's base pose row (constant + default sub-tracks in the output layout, pipeline.cu) depends on besides the clip
+	struct BasePoseKey
+	{
+		uint32_t layout;
+		uint32_t normalize_always;
+		uint32_t default_mode[3];
+		float    constant_defaults[12];
+	};
+
+	struct BasePoseRows
+	{
+		BasePoseKey key;
+		uint8_t* d_rows = nullptr;			// [num_clips][row_stride]
+		uint32_t row_stride = 0;
+		cudaEvent_t ready = nullptr;		// recorded after the build kernel on the stream that asked for it first
+		uint64_t last_use = 0;
+	};
+}
+
 struct aclb200_clipset
 {
 	int device = 0;
@@ -39,6 +61,11 @@ struct aclb200_clipset
 
 	uint8_t* d_data = nullptr;
 	aclb200::ClipDesc* d_clips = nullptr;
+
+	// base pose rows built on first use per (layout, normalisation, default modes, default values), a handful kept
+	mutable std::mutex base_mutex;
+	mutable std::vector<aclb200::BasePoseRows> base_rows;
+	mutable uint64_t base_clock = 0;
 };
 
 namespace aclb200
@@ -72,6 +99,8 @@ namespace aclb200
 		uint32_t grid_blocks;				// pipeline: persistent grid size
 		uint32_t smem_stage_size;			// pipeline: bytes of one stage (key frame windows + poses)
 		float    one;						// 1.0f the compiler cannot see (keeps f32x2 mul + add unfused, see pipeline.cu)
+		const uint8_t* base_poses;			// pipeline: base pose row per clip (nullptr: phase A runs in the kernel)
+		uint32_t base_stride;
 		uint8_t* out;
 		uint64_t pose_stride;
 		uint32_t bone_stride;				// 48 or 40 (transform), components * 4 (scalar)
@@ -105,4 +134,6 @@ namespace aclb200
 	cudaError_t configure_pipeline_kernels(int optin_limit, int& min_available);
 	bool plan_pipeline(DecodeParams& params, uint32_t max_key_frame_bytes, int max_dynamic_smem, int num_sms);
 	cudaError_t launch_transform_pipeline(const DecodeParams& params, cudaStream_t stream);
+	void acquire_base_poses(const aclb200_clipset* clipset, DecodeParams& params, cudaStream_t stream);
+	void release_base_poses(aclb200_clipset* clipset);
 }

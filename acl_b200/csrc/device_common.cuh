@@ -92,6 +92,7 @@ namespace aclb200
 			uint32_t blob_animated_off[2];
 			uint32_t pose_bits[2];
 			uint32_t looping_policy;
+			uint32_t clip;
 		};
 
 		// apply_rounding_policy, core/impl/interpolation_utils.impl.h:261-278
@@ -247,6 +248,7 @@ namespace aclb200
 			const SegDesc seg1 = segs[segment_index1];
 
 			rs.image = image;
+			rs.clip = request.clip;
 			rs.alpha = alpha;
 			rs.num_tracks = clip.num_tracks;
 			rs.clip_flags = clip.flags;
@@ -383,9 +385,12 @@ namespace aclb200
 		// ---------------------------------------------------------------------------------------------------
 		__device__ __forceinline__ Entry load_entry(const ReqState& rs, int k, uint32_t slot)
 		{
-			const uint4 v = __ldg(reinterpret_cast<const uint4*>(rs.image + rs.entries_off[k]) + slot);
+			const uint4* src = reinterpret_cast<const uint4*>(rs.image + rs.entries_off[k]) + slot * 2;
+			const uint4 a = __ldg(src), b = __ldg(src + 1);
 			Entry e;
-			e.offset_code = v.x; e.range_lo = v.y; e.range_hi = v.z; e.inv_max = __uint_as_float(v.w);
+			e.offset_code = a.x; e.inv_max = __uint_as_float(a.y);
+			e.min[0] = __uint_as_float(a.z); e.min[1] = __uint_as_float(a.w); e.min[2] = __uint_as_float(b.x);
+			e.extent[0] = __uint_as_float(b.y); e.extent[1] = __uint_as_float(b.z); e.extent[2] = __uint_as_float(b.w);
 			return e;
 		}
 
@@ -402,9 +407,9 @@ namespace aclb200
 			{
 				// constant inside the segment: the 3 x 16 bit sample was gathered from the segment range bytes at upload
 				// (animated_track_cache.transform.h:552-587; unpack_vector3_u48_unsafe, math/vector4_packing.h:628-653)
-				xi = e.range_lo & 0xFFFFu;
-				yi = e.range_lo >> 16;
-				zi = e.range_hi & 0xFFFFu;
+				xi = __float_as_uint(e.min[0]);
+				yi = __float_as_uint(e.min[1]);
+				zi = __float_as_uint(e.min[2]);
 			}
 			else if (code & k_entry_raw)
 			{
@@ -462,21 +467,11 @@ namespace aclb200
 
 			if ((rs.clip_flags & k_clip_has_segments) && (!SINGLE || !ignore_segment))
 			{
-				float min_x = 0.0f, min_y = 0.0f, min_z = 0.0f, ext_x = 1.0f, ext_y = 1.0f, ext_z = 1.0f;
-				if (!ignore_segment)
-				{
-					// unpack_segment_range_data, :157-298: u8 * (1 / 255)
-					const float n = 1.0f / 255.0f;
-					min_x = fmul(u2f(e.range_lo & 0xFFu), n);
-					min_y = fmul(u2f((e.range_lo >> 8) & 0xFFu), n);
-					min_z = fmul(u2f((e.range_lo >> 16) & 0xFFu), n);
-					ext_x = fmul(u2f(e.range_lo >> 24), n);
-					ext_y = fmul(u2f(e.range_hi & 0xFFu), n);
-					ext_z = fmul(u2f((e.range_hi >> 8) & 0xFFu), n);
-				}
-				x = fmuladd(x, ext_x, min_x);
-				y = fmuladd(y, ext_y, min_y);
-				z = fmuladd(z, ext_z, min_z);
+				// unpack_segment_range_data, :157-298: u8 * (1 / 255), done at upload (layout.h Entry)
+				const bool constant_sample = code == 0;		// its min[] holds the sample integers
+				x = fmuladd(x, e.extent[0], constant_sample ? 0.0f : e.min[0]);
+				y = fmuladd(y, e.extent[1], constant_sample ? 0.0f : e.min[1]);
+				z = fmuladd(z, e.extent[2], constant_sample ? 0.0f : e.min[2]);
 			}
 
 			if (!SINGLE || !ignore_clip)
@@ -511,11 +506,10 @@ namespace aclb200
 			float x = fmul(u2f(xi), e.inv_max), y = fmul(u2f(yi), e.inv_max), z = fmul(u2f(zi), e.inv_max);
 			if (code != 0 && (rs.clip_flags & k_clip_has_segments))
 			{
-				// unpack_vector3_u24_unsafe min then extent, math/vector4_packing.h:781-818
-				const float n = 1.0f / 255.0f;
-				x = fmuladd(x, fmul(u2f(e.range_lo >> 24), n), fmul(u2f(e.range_lo & 0xFFu), n));
-				y = fmuladd(y, fmul(u2f(e.range_hi & 0xFFu), n), fmul(u2f((e.range_lo >> 8) & 0xFFu), n));
-				z = fmuladd(z, fmul(u2f((e.range_hi >> 8) & 0xFFu), n), fmul(u2f((e.range_lo >> 16) & 0xFFu), n));
+				// unpack_vector3_u24_unsafe min then extent, math/vector4_packing.h:781-818 (converted at upload)
+				x = fmuladd(x, e.extent[0], e.min[0]);
+				y = fmuladd(y, e.extent[1], e.min[1]);
+				z = fmuladd(z, e.extent[2], e.min[2]);
 			}
 			// clip range (:949-958)
 			out[0] = fmuladd(x, clip_extent.x, clip_min.x);

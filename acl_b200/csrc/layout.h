@@ -19,10 +19,10 @@
 //                                           it belongs to (the "select" the CPU does by walking the 2-bit type arrays)
 //     start_indices[num_segments + 1] u32   segment_start_indices + sentinel (only when num_segments > 1)
 //     SegDesc[num_segments]           32 B
-//     Entry[num_segments][num_animated_total] 16 B  per segment and sub-track: bit offset inside a key frame (the running sum of
+//     Entry[num_segments][num_animated_total] 32 B  per segment and sub-track: bit offset inside a key frame (the running sum of
 //                                           animated_track_data_bit_offset, animated_track_cache.transform.h:598-599,653), bit
-//                                           width, the 6 segment range bytes (or the constant sample when the bit rate is 0)
-//                                           and 1 / (2^bits - 1)
+//                                           width, 1 / (2^bits - 1) and the segment range as floats (or the constant sample
+//                                           when the bit rate is 0)
 //     stream[num_segments]            u32[] key frames of the segment, byte-swapped words, 16-byte aligned, 64 B zero tail
 #pragma once
 
@@ -117,17 +117,20 @@ namespace aclb200
 
 	// Entry::offset_code = (bit offset inside the key frame << 8) | code
 	//   code 1..23           bits per component, quantised, segment + clip range apply
-	//   code 0               constant inside the segment: range_lo/range_hi hold the 3 x 16 bit sample, only the clip range applies
+	//   code 0               constant inside the segment: min[] holds the 3 x 16 bit sample (as integers), only the clip range applies
 	//   code 32 | k_entry_raw  raw 32-bit floats (3 components, 4 for quatf_full rotations), no range applies
 	constexpr uint32_t k_entry_raw = 0x80u;
 	struct alignas(16) Entry
 	{
 		uint32_t offset_code;
-		uint32_t range_lo;		// code 1..23: min.x | min.y << 8 | min.z << 16 | extent.x << 24      code 0: x | y << 16
-		uint32_t range_hi;		// code 1..23: extent.y | extent.z << 8                               code 0: z
 		float    inv_max;		// 1 / (2^code - 1) (PackedTableEntry::max_value, math/vector4_packing.h:927-929); 1 / 65535 for code 0
+		// code 1..23: the segment range of the sub-track already as floats, u8 * (1 / 255) evaluated in float on the host exactly as
+		// unpack_segment_range_data does (animated_track_cache.transform.h:157-298); code 0: the bit patterns of the three 16 bit
+		// integers of the constant sample sit in min[]; raw: min = 0, extent = 1 (an ignored range still multiplies by 1 and adds 0)
+		float    min[3];
+		float    extent[3];
 	};
-	static_assert(sizeof(Entry) == 16, "Entry is 16 bytes");
+	static_assert(sizeof(Entry) == 32, "Entry is 32 bytes");
 
 	// Scalar clips (decompression/impl/decompression.scalar.h): one descriptor per track.
 	struct alignas(16) ScalarTrackDesc
