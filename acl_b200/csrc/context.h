@@ -98,6 +98,8 @@ namespace aclb200
 		uint32_t out_bulk;					// pipeline: every pose row is 16 byte granular, rows leave shared memory as TMA bulk stores
 		uint32_t grid_blocks;				// pipeline: persistent grid size
 		uint32_t smem_stage_size;			// pipeline: bytes of one stage (key frame windows + poses)
+		uint32_t batch_group;				// pipeline: consecutive batches handed to the blocks that share an SM
+		uint32_t batch_sms;
 		float    one;						// 1.0f the compiler cannot see (keeps f32x2 mul + add unfused, see pipeline.cu)
 		const uint8_t* base_poses;			// pipeline: base pose row per clip (nullptr: phase A runs in the kernel)
 		uint32_t base_stride;
