@@ -370,11 +370,10 @@ def main() -> None:
     gpu_launches = ctx.launch_count - launches_before
     elapsed_ms = start.elapsed_time(stop)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in per_launch]))
-    if distributed:
-        t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-    value = units_per_step * world * args.steps / (elapsed_ms * 1e-3)
+    from acl_b200.sharding import JobReducer
+    reducer = JobReducer(device="cuda")
+    elapsed_ms = reducer.max(elapsed_ms)                                # slowest rank
+    value = reducer.sum(units_per_step * args.steps) / (elapsed_ms * 1e-3)   # every rank's units
 
     # ---- e2e: host buffers through aclb200_decompress_tracks_host ----
     e2e = None
@@ -391,11 +390,8 @@ def main() -> None:
             ctx.decompress_tracks_host(clipset, req_np, options, out_np)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
-        if distributed:
-            t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
-        e2e = {"value": units_per_step * world * e2e_steps / e2e_s, "unit": unit, "h2d_bytes_per_step": int(requests.nbytes),
+        e2e_s = reducer.max(e2e_s)
+        e2e = {"value": reducer.sum(units_per_step * e2e_steps) / e2e_s, "unit": unit, "h2d_bytes_per_step": int(requests.nbytes),
                "d2h_bytes_per_step": int(num_requests * pose_bytes), "steps": e2e_steps}
         del h_out
 
@@ -417,7 +413,7 @@ def main() -> None:
     if os.path.exists(traffic_path):
         traffic = json.load(open(traffic_path)).get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "transform_decompress_tracks_kernel" if is_transform else "scalar_decompress_tracks_kernel",
+                "kernel": "transform_tracks_pipeline_kernel" if is_transform else "scalar_decompress_tracks_kernel",
                 "kernel_ms": kernel_ms, "algorithmic_bytes_in": alg["in_bytes"], "algorithmic_bytes_out": alg["out_bytes"],
                 "bytes_written": int(written_per_step), "peak_source": peak_src}
 

@@ -1,0 +1,106 @@
+"""N > 1 host logic: clips shard across ranks, requests follow their clip, no data-path collective.
+Runs world_size 2 over gloo on the CPU; the per-rank "decode" is the oracle port, which tests may use as the checker."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from acl_b200 import sharding
+from . import clips
+
+NAMES = ["c1_30bones", "mixed_scale", "single_segment", "ragged_17", "looping", "one_bone"]
+
+
+def test_partition_is_contiguous_and_balanced():
+    sizes = [100, 100, 100, 100, 400, 100, 100]
+    owner, local, bounds = sharding.partition_clips(sizes, 2)
+    assert bounds[0][0] == 0 and bounds[-1][1] == len(sizes) and bounds[0][1] == bounds[1][0]
+    assert list(owner) == sorted(owner)
+    for r, (lo, hi) in enumerate(bounds):
+        assert list(local[lo:hi]) == list(range(hi - lo))
+        assert all(owner[lo:hi] == r)
+    shard_bytes = [sum(sizes[lo:hi]) for lo, hi in bounds]
+    assert max(shard_bytes) <= 0.75 * sum(sizes)
+    # more ranks than clips: the extra ranks get empty shards, nothing is lost
+    owner, local, bounds = sharding.partition_clips([10, 10], 4)
+    assert sum(hi - lo for lo, hi in bounds) == 2
+
+
+def test_route_requests_covers_every_request_once():
+    owner, local, bounds = sharding.partition_clips([5, 5, 5, 5, 5], 2)
+    req_clip = np.array([4, 0, 2, 9, 1, 3, 0], dtype=np.uint32)       # 9 is out of range
+    req_time = np.arange(7, dtype=np.float32)
+    seen = []
+    for rank in range(2):
+        positions, local_clip, times = sharding.route_requests(req_clip, req_time, owner, local, rank)
+        seen += list(positions)
+        for p, lc, t in zip(positions, local_clip, times):
+            assert t == req_time[p]
+            if req_clip[p] < 5:
+                assert owner[req_clip[p]] == rank and local[req_clip[p]] == lc
+            else:
+                assert rank == 0 and lc == 0xFFFFFFFF
+    assert sorted(seen) == list(range(7))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, result_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import port as oracle_port
+        blobs = [clips.load_blob(n) for n in NAMES]
+        specs = [clips.TRANSFORM_SPECS[n] for n in NAMES]
+        owner, local, bounds = sharding.partition_clips([b.nbytes for b in blobs], world)
+        # the global request list every rank sees
+        rng = np.random.default_rng(5)
+        req_clip = rng.integers(0, len(NAMES), 64).astype(np.uint32)
+        req_time = np.array([rng.uniform(-0.1, (specs[c].num_samples - 1) / specs[c].sample_rate + 0.1) for c in req_clip], dtype=np.float32)
+        positions, local_clip, times = sharding.route_requests(req_clip, req_time, owner, local, rank)
+        # this rank's clip set is the slice bounds[rank] of the table; decode its requests (oracle = the checker's decode)
+        lo, hi = bounds[rank]
+        my_blobs = blobs[lo:hi]
+        settings = oracle_port.settings_for_kind(0)
+        max_tracks = max(s.num_tracks for s in specs)
+        rows = np.zeros((len(positions), max_tracks, 12), np.float32)
+        for i, (lc, t) in enumerate(zip(local_clip, times)):
+            pose = oracle_port.transform_decompress_tracks(my_blobs[lc], settings, t, 0)
+            rows[i, :pose.shape[0]] = pose
+        # host-side gather of the results (NOT part of the product data path: poses normally stay on the GPU that made them)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (positions, rows))
+        merged = sharding.scatter_results(len(req_clip), (max_tracks, 12), [g[0] for g in gathered], [g[1] for g in gathered])
+        # whole-job numbers
+        reducer = sharding.JobReducer()
+        reducer.barrier()
+        seconds = 1.0 + rank          # pretend rank 1 was slower
+        job = reducer.throughput(float(len(positions)), seconds)
+        if rank == 0:
+            expected = np.zeros_like(merged)
+            for i, (c, t) in enumerate(zip(req_clip, req_time)):
+                pose = oracle_port.transform_decompress_tracks(blobs[c], settings, t, 0)
+                expected[i, :pose.shape[0]] = pose
+            ok = np.array_equal(expected.view(np.uint32), merged.view(np.uint32))
+            np.save(result_path, np.array([1.0 if ok else 0.0, job, float(sum(len(g[0]) for g in gathered))]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharded_decode_matches_single_process(tmp_path):
+    world = 2
+    result_path = str(tmp_path / "result.npy")
+    mp.spawn(_worker, args=(world, _free_port(), result_path), nprocs=world, join=True)
+    ok, job, total = np.load(result_path)
+    assert ok == 1.0
+    assert total == 64
+    assert job == pytest.approx(64 / 2.0)      # all units over the slowest rank's time
