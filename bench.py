@@ -195,14 +195,34 @@ def algorithmic_bytes_scalar(w) -> dict:
 # clocks under load
 # ------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region: an NVML polling thread (1 ms period, samples stamped with the host
+    clock and filtered to the region), falling back to `nvidia-smi -lms` when the NVML binding is missing."""
     QUERY = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, device_index: int):
         self.device_index = device_index
         self.proc = None
         self.lines: list[str] = []
+        self.nvml = None
+        self.samples: list[tuple[float, int, int]] = []
+        self.running = False
+        self.window = (0.0, float("inf"))
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = int(visible.split(",")[self.device_index]) if visible and visible.replace(",", "").isdigit() else self.device_index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.running = True
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.device_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -211,11 +231,39 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nvml = self.nvml
+        reasons_fn = getattr(nvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while self.running:
+            try:
+                self.samples.append((time.perf_counter(), int(nvml.nvmlDeviceGetClockInfo(self.handle, nvml.NVML_CLOCK_SM)), int(reasons_fn(self.handle))))
+            except Exception:
+                pass
+            time.sleep(0.001)
+
+    def mark(self, begin: float, end: float):
+        """Host clock stamps (time.perf_counter) bracketing the timed region."""
+        self.window = (begin, end)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self.running = False
+            self.thread.join(timeout=1)
+            nvml = self.nvml
+            inside = [s for s in self.samples if self.window[0] <= s[0] <= self.window[1]]
+            if not inside:
+                return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["no samples"]}
+            masks = {"hw_slowdown": getattr(nvml, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nvml, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nvml, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nvml, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            reasons = sorted(label for label, mask in masks.items() if any(s[2] & mask for s in inside))
+            return {"sm_mhz": float(np.median([s[1] for s in inside])), "sm_max_mhz": float(self.sm_max), "reasons": reasons,
+                    "samples": len(inside), "source": "nvml, 1 ms polling inside the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -273,6 +321,7 @@ def main() -> None:
     ap.add_argument("--clips", type=int, default=None, help="override the number of clips per GPU (debugging)")
     ap.add_argument("--layout", default="qvv40", choices=["qvv40", "qvv48"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather", action="store_true", help="N > 1: also time decode + NCCL all-gather of the poses (SURVEY 8e, optional consumer-side gather)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -359,6 +408,7 @@ def main() -> None:
     stop = torch.cuda.Event(enable_timing=True)
     per_launch = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    host_begin = time.perf_counter()
     start.record(stream)
     for a, b in per_launch:
         a.record(stream)
@@ -366,14 +416,35 @@ def main() -> None:
         b.record(stream)
     stop.record(stream)
     barrier()
+    sampler.mark(host_begin, time.perf_counter())
     clocks = sampler.stop()
     gpu_launches = ctx.launch_count - launches_before
     elapsed_ms = start.elapsed_time(stop)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in per_launch]))
+    kernel_ms = float(np.median([a.elapsed_time(b) for a, b in per_launch]))     # median launch, CUDA events on the launch stream
     from acl_b200.sharding import JobReducer
     reducer = JobReducer(device="cuda")
     elapsed_ms = reducer.max(elapsed_ms)                                # slowest rank
     value = reducer.sum(units_per_step * args.steps) / (elapsed_ms * 1e-3)   # every rank's units
+
+    # ---- optional: every rank ends up with every pose (one NCCL all-gather after the decode; not part of the decode path) ----
+    gather = None
+    if distributed and args.gather:
+        gathered = torch.empty(world * d_out.numel(), dtype=torch.uint8, device="cuda")
+        for _ in range(2):
+            launch()
+            dist.all_gather_into_tensor(gathered, d_out)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for _ in range(args.steps):
+            launch()
+            dist.all_gather_into_tensor(gathered, d_out)
+        g1.record(stream)
+        barrier()
+        gather_ms = reducer.max(g0.elapsed_time(g1))
+        gather = {"value": reducer.sum(units_per_step * args.steps) / (gather_ms * 1e-3), "unit": unit,
+                  "bytes_gathered_per_step_per_gpu": int(world * d_out.numel()), "collective": "ncclAllGather of the pose buffers"}
+        del gathered
 
     # ---- e2e: host buffers through aclb200_decompress_tracks_host ----
     e2e = None
@@ -444,7 +515,7 @@ def main() -> None:
                    "requests_per_step_per_gpu": num_requests, "bones": w["num_tracks"], "layout": args.layout,
                    "l2": f"inputs larger than L2: {clipset.blob_bytes / 1e6:.0f} MB compressed + {num_requests * pose_bytes / 1e6:.0f} MB of poses per step vs 126 MB L2",
                    "math": "exact (bit-identical to the reference)", "parallelism": f"clip-sharded x{world}, no data-path collective"},
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gather": gather, "gpu_launches": int(gpu_launches), "clocks": clocks,
     }
     print(json.dumps(result))
     if distributed:

@@ -204,6 +204,73 @@ namespace acl_b200
 		aclb200_clipset_info m_info = {};
 	};
 
+	// Where a batch writes its poses: device memory, request r at d_poses + r * pose_stride_bytes (0 = packed)
+	struct device_pose_writer : track_writer
+	{
+		void* d_poses = nullptr;
+		uint32_t output_layout = ACLB200_LAYOUT_QVV48;
+		uint64_t pose_stride_bytes = 0;
+		void* stream = nullptr;		// cudaStream_t
+	};
+
+	// The batched form of decompression_context<settings>: bind N clips, seek N' (clip, time) requests, decode them in one launch.
+	// The settings type plays the role it plays in the reference (decompress.h:76-88): it fixes the normalisation policy, wrapping,
+	// per track rounding and sample time clamping at compile time.
+	template<class settings_type = default_transform_decompression_settings>
+	class batch_context
+	{
+	public:
+		explicit batch_context(device_context& device) : m_batch(device) {}
+
+		// initialize() for every clip of the batch; false (and the offending index) when one is not a valid compressed_tracks
+		bool bind(const void* const* compressed_tracks, const uint32_t* sizes, uint32_t num_clips, uint32_t* out_failed_clip = nullptr)
+		{
+			m_num_requests = 0;
+			return m_batch.upload(compressed_tracks, sizes, num_clips, true, out_failed_clip);
+		}
+		void reset() { m_batch.release(); m_num_requests = 0; }
+		bool is_initialized() const { return m_batch.clipset() != nullptr; }
+		uint32_t get_num_clips() const { return m_batch.info().num_clips; }
+		uint32_t get_max_num_tracks() const { return m_batch.info().max_tracks; }
+		void set_looping_policy(sample_looping_policy policy) { m_looping = policy; }
+		sample_looping_policy get_looping_policy() const { return m_looping; }
+
+		// seek() for a batch: d_requests is a DEVICE array of { clip index, sample_time }; evaluated on the GPU with the decode
+		void seek(const aclb200_request* d_requests, uint32_t num_requests, sample_rounding_policy rounding_policy)
+		{
+			m_requests = d_requests;
+			m_num_requests = num_requests;
+			m_rounding = rounding_policy;
+		}
+
+		// decompress_tracks() for the batch, asynchronous on writer.stream
+		template<class writer_type>
+		void decompress_tracks(const writer_type& writer, const uint8_t* d_per_track_rounding = nullptr, const float* d_variable_defaults = nullptr)
+		{
+			if (!is_initialized() || m_num_requests == 0)
+				return;
+			aclb200_options options = make_options<settings_type>(writer, m_rounding, m_looping);
+			// unlike the one pose shim, variable defaults live on the device here
+			options.default_rotation_mode = static_cast<uint32_t>(writer_type::get_default_rotation_mode());
+			options.default_translation_mode = static_cast<uint32_t>(writer_type::get_default_translation_mode());
+			options.default_scale_mode = static_cast<uint32_t>(writer_type::get_default_scale_mode());
+			options.d_variable_defaults = d_variable_defaults;
+			options.d_per_track_rounding = d_per_track_rounding;
+			options.output_layout = writer.output_layout;
+			options.pose_stride_bytes = writer.pose_stride_bytes;
+			m_batch.decompress_tracks(m_requests, m_num_requests, options, writer.d_poses, writer.stream);
+		}
+
+		batch_decompressor& decompressor() { return m_batch; }
+
+	private:
+		batch_decompressor m_batch;
+		const aclb200_request* m_requests = nullptr;
+		uint32_t m_num_requests = 0;
+		sample_looping_policy m_looping = sample_looping_policy::as_compressed;
+		sample_rounding_policy m_rounding = sample_rounding_policy::none;
+	};
+
 	// Drop-in for acl::decompression_context<settings> on transform clips: one clip bound, one pose per decompress_tracks().
 	template<class settings_type = default_transform_decompression_settings>
 	class decompression_context

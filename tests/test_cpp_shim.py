@@ -12,11 +12,13 @@ from . import clips
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def build_shim_program(tmp_path):
-    exe = str(tmp_path / "shim_decode")
+def build_shim_program(tmp_path, name="shim_decode", cuda_runtime=False):
+    exe = str(tmp_path / name)
     lib_dir = os.path.join(ROOT, "acl_b200")
-    cmd = ["g++", "-std=c++14", "-O1", "-Wall", "-Wextra", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "cpp", "shim_decode.cpp"),
+    cmd = ["g++", "-std=c++14", "-O1", "-Wall", "-Wextra", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "cpp", name + ".cpp"),
            "-L" + lib_dir, "-laclb200", "-Wl,-rpath," + lib_dir]
+    if cuda_runtime:
+        cmd += ["-I/usr/local/cuda/include", "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath,/usr/local/cuda/lib64"]
     subprocess.run(cmd, check=True, capture_output=True, text=True)
     return exe
 
@@ -51,3 +53,34 @@ def test_shim_decode_matches_oracle(tmp_path, oracle_port, name):
     for i, t in enumerate(times):
         expected = oracle_port.transform_decompress_tracks(blob, settings, np.float32(t), 0)
         assert np.array_equal(expected[:, clips.DEFINED_LANES].view(np.uint32), got[i][:, clips.DEFINED_LANES]), (name, t)
+
+
+def test_batch_shim_compiles(tmp_path):
+    build_shim_program(tmp_path, "shim_batch", cuda_runtime=True)
+
+
+@pytest.mark.gpu
+def test_batch_context_matches_oracle(tmp_path, oracle_port):
+    """batch_context<default settings>: bind several clips, one launch for a ragged request list in device memory."""
+    exe = build_shim_program(tmp_path, "shim_batch", cuda_runtime=True)
+    names = ["c1_30bones", "ragged_17", "mixed_scale", "one_bone"]
+    blobs = [clips.load_blob(n) for n in names]
+    specs = [clips.TRANSFORM_SPECS[n] for n in names]
+    rng = np.random.default_rng(3)
+    req_clip = rng.integers(0, len(names), 24)
+    req_time = [float(np.float32(rng.uniform(-0.1, (specs[c].num_samples - 1) / specs[c].sample_rate + 0.1))) for c in req_clip]
+    args = [exe, str(len(names))] + [os.path.join(ROOT, "tests", "golden", n + ".acl.bin") for n in names]
+    for c, t in zip(req_clip, req_time):
+        args += [str(int(c)), repr(t)]
+    result = subprocess.run(args, capture_output=True, text=True, check=True)
+    max_tracks = max(s.num_tracks for s in specs)
+    got = np.zeros((len(req_clip), max_tracks, 12), np.uint32)
+    for line in result.stdout.strip().splitlines():
+        r = line.split()
+        got[int(r[0]), int(r[1])] = [int(w, 16) for w in r[2:]]
+    settings = oracle_port.settings_for_kind(0)
+    for i, (c, t) in enumerate(zip(req_clip, req_time)):
+        expected = oracle_port.transform_decompress_tracks(blobs[c], settings, np.float32(t), 0)
+        n = expected.shape[0]
+        assert np.array_equal(expected[:, clips.DEFINED_LANES].view(np.uint32), got[i][:n][:, clips.DEFINED_LANES]), (names[c], t)
+        assert not got[i][n:].any()       # bones past the clip's own track count are left untouched
