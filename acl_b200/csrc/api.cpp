@@ -264,7 +264,7 @@ extern "C"
 				const bool rows_16 = options->output_layout == ACLB200_LAYOUT_QVV48 || clipset->all_tracks_even;
 				pipeline_params.out_bulk = rows_16 && ((uint64_t(reinterpret_cast<uintptr_t>(d_out)) | pipeline_params.pose_stride) & 15) == 0 ? 1u : 0u;
 				acquire_base_poses(clipset, pipeline_params, static_cast<cudaStream_t>(stream));
-				return finish_launch(context, launch_transform_pipeline(pipeline_params, static_cast<cudaStream_t>(stream)), "decompress_tracks (pipeline)");
+				return finish_launch(context, launch_transform_pipeline(pipeline_params, options->math_mode, static_cast<cudaStream_t>(stream)), "decompress_tracks (pipeline)");
 			}
 		}
 		return finish_launch(context, launch_transform_decompress_tracks(params, options->math_mode, static_cast<cudaStream_t>(stream)), "decompress_tracks");

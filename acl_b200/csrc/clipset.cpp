@@ -412,7 +412,9 @@ namespace aclb200
 								}
 							}
 						}
-						std::memcpy(image.at(d.anim_table_offset) + size_t(slot) * sizeof(AnimDesc), &anim, sizeof(anim));
+						// stored as two arrays of 16 byte halves (layout.h): a warp's loads of consecutive sub-tracks are then contiguous
+						std::memcpy(image.at(d.anim_table_offset) + size_t(slot) * 16, &anim, 16);
+						std::memcpy(image.at(d.anim_table_offset) + (size_t(num_animated_total) + slot) * 16, reinterpret_cast<const uint8_t*>(&anim) + 16, 16);
 					}
 			}
 
@@ -559,7 +561,8 @@ namespace aclb200
 						if (bit_offset >= (1u << 24))
 							return "key frame too large for the sub-track entry table";
 						entry.offset_code = (bit_offset << 8) | code;
-						std::memcpy(image.at(seg.entries_offset) + size_t(slot) * sizeof(Entry), &entry, sizeof(entry));
+						std::memcpy(image.at(seg.entries_offset) + size_t(slot) * 16, &entry, 16);
+						std::memcpy(image.at(seg.entries_offset) + (size_t(num_animated_total) + slot) * 16, reinterpret_cast<const uint8_t*>(&entry) + 16, 16);
 						bit_offset += stream_bits;
 					}
 					if (bit_offset > pose_bit_size && num_animated[kind] != 0)

@@ -135,7 +135,7 @@ namespace aclb200
 	// pipeline.cu
 	cudaError_t configure_pipeline_kernels(int optin_limit, int& min_available);
 	bool plan_pipeline(DecodeParams& params, uint32_t max_key_frame_bytes, int max_dynamic_smem, int num_sms);
-	cudaError_t launch_transform_pipeline(const DecodeParams& params, cudaStream_t stream);
+	cudaError_t launch_transform_pipeline(const DecodeParams& params, uint32_t math_mode, cudaStream_t stream);
 	void acquire_base_poses(const aclb200_clipset* clipset, DecodeParams& params, cudaStream_t stream);
 	void release_base_poses(aclb200_clipset* clipset);
 }

@@ -385,8 +385,9 @@ namespace aclb200
 		// ---------------------------------------------------------------------------------------------------
 		__device__ __forceinline__ Entry load_entry(const ReqState& rs, int k, uint32_t slot)
 		{
-			const uint4* src = reinterpret_cast<const uint4*>(rs.image + rs.entries_off[k]) + slot * 2;
-			const uint4 a = __ldg(src), b = __ldg(src + 1);
+			// two arrays of 16 byte halves (layout.h)
+			const uint4* src = reinterpret_cast<const uint4*>(rs.image + rs.entries_off[k]) + slot;
+			const uint4 a = __ldg(src), b = __ldg(src + (rs.num_animated[0] + rs.num_animated[1] + rs.num_animated[2]));
 			Entry e;
 			e.offset_code = a.x; e.inv_max = __uint_as_float(a.y);
 			e.min[0] = __uint_as_float(a.z); e.min[1] = __uint_as_float(a.w); e.min[2] = __uint_as_float(b.x);
@@ -645,9 +646,9 @@ namespace aclb200
 		template<int NORM, bool PER_TRACK, bool SINGLE, bool STAGED>
 		__device__ __forceinline__ uint32_t animated_rotation(const DecodeParams& p, const ReqState& rs, const uint32_t* s_stage, uint32_t rank, float alpha_in, float rotation[4])
 		{
-			const float4* anim = reinterpret_cast<const float4*>(rs.image + rs.anim_off) + size_t(rank) * 2;
-			const float4 clip_extent = __ldg(anim + 0);		// .w carries the bone index
-			const float4 clip_min = __ldg(anim + 1);
+			const float4* anim = reinterpret_cast<const float4*>(rs.image + rs.anim_off) + rank;
+			const float4 clip_extent = __ldg(anim);		// .w carries the bone index
+			const float4 clip_min = __ldg(anim + (rs.num_animated[0] + rs.num_animated[1] + rs.num_animated[2]));
 			const uint32_t bone = __float_as_uint(clip_extent.w);
 			const Entry e0 = load_entry(rs, 0, rank);
 			const Entry e1 = rs.single_segment ? e0 : load_entry(rs, 1, rank);
@@ -668,9 +669,9 @@ namespace aclb200
 		__device__ __forceinline__ uint32_t animated_vector(const DecodeParams& p, const ReqState& rs, const uint32_t* s_stage, uint32_t kind, uint32_t rank, float alpha_in, float value[3])
 		{
 			const uint32_t slot = rs.num_animated[0] + (kind == 2 ? rs.num_animated[1] : 0u) + rank;
-			const float4* anim = reinterpret_cast<const float4*>(rs.image + rs.anim_off) + size_t(slot) * 2;
-			const float4 clip_extent = __ldg(anim + 0);
-			const float4 clip_min = __ldg(anim + 1);
+			const float4* anim = reinterpret_cast<const float4*>(rs.image + rs.anim_off) + slot;
+			const float4 clip_extent = __ldg(anim);
+			const float4 clip_min = __ldg(anim + (rs.num_animated[0] + rs.num_animated[1] + rs.num_animated[2]));
 			const uint32_t bone = __float_as_uint(clip_extent.w);
 			const Entry e0 = load_entry(rs, 0, slot);
 			const Entry e1 = rs.single_segment ? e0 : load_entry(rs, 1, slot);

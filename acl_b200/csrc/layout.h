@@ -92,6 +92,9 @@ namespace aclb200
 	constexpr uint32_t k_max_tracks = 1u << 18;					// the scale rank has 18 bits left
 
 	// Clip-level data of one animated sub-track: two 16 byte loads give the clip range and the destination bone.
+	// In the image the table is stored as two arrays, first16[num_animated_total] then second16[num_animated_total] (same for Entry):
+	// the threads of a warp handle consecutive sub-tracks, so each of their 16 byte loads covers one contiguous 512 byte run
+	// (4 L1 wavefronts) instead of every other 16 bytes of a 1 KB run (8 wavefronts) -- the L1 data pipe is this kernel's busiest unit.
 	struct alignas(16) AnimDesc
 	{
 		float    extent[3];		// clip range extent xyz (1.0 when the format carries no clip range)

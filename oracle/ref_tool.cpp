@@ -90,6 +90,7 @@ extern "C"
 		uint32_t strip_trivial;
 		float    strip_proportion;
 		float    strip_threshold;
+		float    rotation_offset;		// radians added to every animated rotation angle (pi => W crosses 0, the ill-conditioned end of W reconstruction)
 	};
 
 	struct aclref_scalar_spec
@@ -222,7 +223,7 @@ namespace
 				else if (rot_kind == 2)
 				{
 					const double activity = (rot_partial && sample * 3 >= num_samples) ? 0.0 : 1.0;
-					double angle = rot_base + activity * (0.6 * std::sin(rot_freq * tt + rot_phase) + 0.05 * std::sin(rot_freq2 * tt + rot_phase2));
+					double angle = double(spec.rotation_offset) + rot_base + activity * (0.6 * std::sin(rot_freq * tt + rot_phase) + 0.05 * std::sin(rot_freq2 * tt + rot_phase2));
 					if (rot_noisy && !looped_last)
 						angle += noise.range(-0.3, 0.3);
 					transform.rotation = make_rotation(axis, angle);

@@ -50,6 +50,8 @@ TRANSFORM_SPECS: dict[str, ref.TransformSpec] = {
     "all_default": T(num_tracks=16, num_samples=40, seed=21, rot_default_pct=100, trans_default_pct=100),
     "ragged_17": T(num_tracks=17, num_samples=47, seed=22, rot_constant_pct=25, trans_constant_pct=25, scale_default_pct=40, scale_constant_pct=30),
     "paragon_like": T(num_tracks=540, num_samples=60, seed=3000, scale_default_pct=95, scale_constant_pct=0),
+    # rotations around half a turn: W crosses 0, where quat_from_positive_w4 is ill-conditioned (1 ulp on x moves W by ulp / W)
+    "half_turn": T(num_tracks=64, num_samples=60, seed=23, rotation_offset=3.0, trans_constant_pct=60),
 }
 
 SCALAR_SPECS: dict[str, ref.ScalarSpec] = {

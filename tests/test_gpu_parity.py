@@ -360,6 +360,41 @@ def test_upload_rejects_what_initialize_rejects(gpu):
     assert err.value.status == 3                            # mixed track types
 
 
+FAST_MATH_TOLERANCE = 1e-5      # BASELINE.json north star: "within 1e-5 on the float QVV components"
+
+
+@pytest.mark.parametrize("name", ["c1_30bones", "c2_100bones", "c5_30x32", "mixed_scale", "looping", "stripped_loop", "noisy_raw", "half_turn", "paragon_like"])
+def test_fast_math_within_tolerance(gpu, name):
+    """ACLB200_MATH_FAST (hardware sqrt / rsqrt, fused multiply-adds after the W reconstruction input): rotations within 1e-5 absolute
+    of the reference on every component -- including `half_turn`, whose W crosses 0 -- translations and scales still bit-exact."""
+    port, ab, ctx = gpu["port"], gpu["ab"], gpu["ctx"]
+    spec = clips.TRANSFORM_SPECS[name]
+    blob = clips.load_blob(name)
+    clipset = ctx.upload([blob], check_hash=True)
+    duration = (spec.num_samples - 1) / spec.sample_rate
+    times = np.concatenate([clips.sample_times(spec), np.linspace(0.0, duration, 97, dtype=np.float32)])
+    zeros = np.zeros(len(times), dtype=np.uint32)
+    n = clipset.max_tracks
+    worst = 0.0
+    for kind in (0, 3):     # default settings (lerp_only) and never-normalise: the two policies the fast arithmetic serves
+        settings = port.settings_for_kind(kind)
+        for rounding in (0, 3):
+            for layout in (ab.LAYOUT_QVV48, ab.LAYOUT_QVV40):
+                got = _decode(gpu, clipset, zeros, times, _options(gpu, settings, rounding_policy=rounding, math_mode=ab.MATH_FAST, output_layout=layout))
+                if layout == ab.LAYOUT_QVV40:
+                    got = got[:, :, :10]
+                for i, t in enumerate(times):
+                    want = port.transform_decompress_tracks(blob, settings, float(t), rounding)
+                    want = want[:, LANES] if layout == ab.LAYOUT_QVV40 else want
+                    rot_error = float(np.abs(got[i, :n, :4] - want[:, :4]).max())
+                    worst = max(worst, rot_error)
+                    assert rot_error <= FAST_MATH_TOLERANCE, (name, kind, rounding, float(t), rot_error)
+                    vec = slice(4, 10) if layout == ab.LAYOUT_QVV40 else [4, 5, 6, 8, 9, 10]
+                    assert clips.bit_equal(got[i, :n][:, vec], want[:, vec]), (name, kind, rounding, float(t))
+    assert worst < 2e-6, worst      # what the approximations actually cost on unit quaternions
+    clipset.release()
+
+
 @pytest.fixture(scope="module")
 def c2_full(gpu):
     """BASELINE.json configs[1] at full size: 10 000 clips x 100 bones x 60 samples, 600 000 requests. Clips come from the reference
@@ -408,6 +443,14 @@ def test_full_size_c2_properties(gpu, c2_full):
     torch.cuda.synchronize()
     assert torch.equal(d_out48[:, :, LANES].contiguous().view(torch.int32), d_out.view(torch.int32))
     del d_out48
+
+    # (4b) fast arithmetic: every component of all 60 M bone-poses within 1e-5 of the bit-exact result, vectors identical
+    d_fast = torch.zeros_like(d_out)
+    ctx.decompress_tracks(clipset, d_requests, n_req, ab.Options(output_layout=ab.LAYOUT_QVV40, math_mode=ab.MATH_FAST), d_fast)
+    torch.cuda.synchronize()
+    assert float((d_fast[:, :, :4] - d_out[:, :, :4]).abs().max()) <= FAST_MATH_TOLERANCE
+    assert torch.equal(d_fast[:, :, 4:].contiguous().view(torch.int32), d_out[:, :, 4:].contiguous().view(torch.int32))
+    del d_fast
 
     # (5) bit-exact against the oracle on a random sample + the very first and last requests
     rng = np.random.default_rng(2)
