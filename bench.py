@@ -51,7 +51,7 @@ def log(*a):
 # ------------------------------------------------------------------------------------------------------------------
 # workload synthesis (never timed)
 # ------------------------------------------------------------------------------------------------------------------
-def make_workload(name: str, rank: int, clips_override: int | None):
+def make_workload(name: str, rank: int, clips_override: int | None, world: int = 1):
     kind, num_clips, bones, samples, description = WORKLOADS[name]
     if clips_override:
         num_clips = clips_override
@@ -63,7 +63,8 @@ def make_workload(name: str, rank: int, clips_override: int | None):
             if name == "c3":
                 spec.scale_default_pct, spec.scale_constant_pct = 95, 0       # 5 % animated scale
             t0 = time.time()
-            buffer, offsets, sizes = ref.compress_transform_batch(spec, num_clips)
+            # the ranks of one box share its host cores
+            buffer, offsets, sizes = ref.compress_transform_batch(spec, num_clips, num_threads=max(1, (os.cpu_count() or 1) // max(world, 1)))
             log(f"[bench] rank {rank}: compressed {num_clips} clips with the reference in {time.time() - t0:.1f} s ({buffer.size / 1e6:.1f} MB)")
         else:
             buffer, offsets, sizes = replicate_golden(GOLDEN_FALLBACK[name], num_clips)
@@ -380,7 +381,7 @@ def main() -> None:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    w = make_workload(args.workload, rank, args.clips)
+    w = make_workload(args.workload, rank, args.clips, world)
     is_transform = w["kind"] == "transform"
     ctx = ab.Context(local_rank)
     clipset = ctx.upload_packed(w["buffer"], w["offsets"], w["sizes"])
