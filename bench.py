@@ -410,12 +410,11 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()             # before the warm-up: NVML initialisation must not eat the (milliseconds long) timed region
     for _ in range(args.warmup):
         launch()
     barrier()
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches_before = ctx.launch_count
     start = torch.cuda.Event(enable_timing=True)
     stop = torch.cuda.Event(enable_timing=True)
