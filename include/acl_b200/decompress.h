@@ -30,6 +30,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 namespace acl_b200
@@ -219,6 +220,8 @@ namespace acl_b200
 	template<class settings_type = default_transform_decompression_settings>
 	class batch_context
 	{
+		static_assert(std::is_base_of<decompression_settings, settings_type>::value, "settings_type must derive from decompression_settings");
+
 	public:
 		explicit batch_context(device_context& device) : m_batch(device) {}
 
@@ -275,6 +278,8 @@ namespace acl_b200
 	template<class settings_type = default_transform_decompression_settings>
 	class decompression_context
 	{
+		static_assert(std::is_base_of<decompression_settings, settings_type>::value, "settings_type must derive from decompression_settings");		// decompress.h:197
+
 	public:
 		explicit decompression_context(device_context& device) : m_batch(device) {}
 
@@ -294,6 +299,21 @@ namespace acl_b200
 			m_pose.assign(size_t(m_batch.info().max_tracks) * 12, 0.0F);
 			return true;
 		}
+		// relocated(const compressed_tracks&), decompress.impl.h:131-156: the clip moved in host memory; the device copy is unaffected
+		bool relocated(const void* compressed_tracks)
+		{
+			if (m_bound == nullptr || compressed_tracks == nullptr)
+				return false;
+			m_bound = compressed_tracks;
+			return true;
+		}
+		void reset()		// decompress.h:120-124
+		{
+			m_batch.release();
+			m_bound = nullptr;
+			m_has_seeked = false;
+		}
+		const void* get_compressed_tracks() const { return m_bound; }
 		bool is_initialized() const { return m_bound != nullptr; }
 		bool is_bound_to(const void* compressed_tracks) const { return m_bound != nullptr && m_bound == compressed_tracks; }	// decompress.impl.h:158-177 compares pointer + hash; the hash was verified at upload
 		void set_looping_policy(sample_looping_policy policy) { m_looping = policy; }
