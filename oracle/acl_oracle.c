@@ -231,6 +231,13 @@ static void find_linear_interpolation_samples_with_sample_rate(uint32_t num_samp
 	*out_alpha = apply_rounding_policy(alpha, rounding_policy);
 }
 
+/* exported so that the reference's own known-answer table (tests/sources/core/test_interpolation_utils.cpp:225-331) can be replayed */
+void aclo_find_key_frames(uint32_t num_samples, float sample_rate, float sample_time, uint32_t rounding_policy, uint32_t looping_policy,
+	uint32_t* out_index0, uint32_t* out_index1, float* out_alpha)
+{
+	find_linear_interpolation_samples_with_sample_rate(num_samples, sample_rate, sample_time, rounding_policy, looping_policy, out_index0, out_index1, out_alpha);
+}
+
 /* core/impl/interpolation_utils.impl.h:224-253 */
 static float find_linear_interpolation_alpha(float sample_index, uint32_t index0, uint32_t index1, uint32_t rounding_policy)
 {

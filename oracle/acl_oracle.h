@@ -75,6 +75,10 @@ int aclo_validate(const void* blob, size_t size, int check_hash);
 
 uint32_t aclo_hash32(const void* data, size_t size);
 
+/* find_linear_interpolation_samples_with_sample_rate, core/impl/interpolation_utils.impl.h:143-201 */
+void aclo_find_key_frames(uint32_t num_samples, float sample_rate, float sample_time, uint32_t rounding_policy, uint32_t looping_policy,
+	uint32_t* out_index0, uint32_t* out_index1, float* out_alpha);
+
 /* Transform (qvvf) path. All functions return 0 on success, <0 on invalid input. */
 int aclo_transform_seek(const void* blob, const aclo_settings* settings, float sample_time,
 	uint32_t rounding_policy, uint32_t looping_policy, aclo_seek_state* out_state);

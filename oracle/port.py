@@ -134,6 +134,16 @@ def validate(blob: np.ndarray, check_hash: bool = False) -> int:
     return lib().aclo_validate(blob.ctypes.data, blob.size, int(check_hash))
 
 
+def find_key_frames(num_samples: int, sample_rate: float, sample_time: float, rounding=ROUND_NONE, looping=LOOP_CLAMP):
+    """find_linear_interpolation_samples_with_sample_rate: (key frame 0, key frame 1, alpha)."""
+    k0, k1, alpha = C.c_uint32(), C.c_uint32(), C.c_float()
+    fn = lib().aclo_find_key_frames
+    fn.restype = None
+    fn.argtypes = [C.c_uint32, C.c_float, C.c_float, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+    fn(num_samples, sample_rate, sample_time, rounding, looping, C.byref(k0), C.byref(k1), C.byref(alpha))
+    return k0.value, k1.value, alpha.value
+
+
 def transform_seek(blob, settings: SettingsBuilder, t: float, rounding=ROUND_NONE, looping=LOOP_AS_COMPRESSED) -> SeekState:
     st = SeekState()
     rc = lib().aclo_transform_seek(blob.ctypes.data, C.byref(settings.c), t, rounding, looping, C.byref(st))
