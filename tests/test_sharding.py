@@ -104,3 +104,39 @@ def test_two_rank_sharded_decode_matches_single_process(tmp_path):
     assert ok == 1.0
     assert total == 64
     assert job == pytest.approx(64 / 2.0)      # all units over the slowest rank's time
+
+
+def test_partition_and_routing_properties():
+    """Property test: any sizes / world / request list -> contiguous cover, every request routed exactly once to the owner of its clip."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(sizes=st.lists(st.integers(min_value=1, max_value=10_000), min_size=0, max_size=40),
+           world=st.integers(min_value=1, max_value=9),
+           picks=st.lists(st.integers(min_value=0, max_value=60), min_size=0, max_size=80))
+    def check(sizes, world, picks):
+        owner, local, bounds = sharding.partition_clips(sizes, world)
+        assert len(bounds) == world and bounds[0][0] == 0 and bounds[-1][1] == len(sizes)
+        for r in range(world - 1):
+            assert bounds[r][1] == bounds[r + 1][0]
+        for r, (lo, hi) in enumerate(bounds):
+            assert all(owner[lo:hi] == r) and list(local[lo:hi]) == list(range(hi - lo))
+        if sizes:
+            # no shard is heavier than its fair share plus one clip
+            fair = sum(sizes) / world
+            assert max(sum(sizes[lo:hi]) for lo, hi in bounds) <= fair + max(sizes)
+        req_clip = np.array(picks, dtype=np.uint32)
+        req_time = np.arange(len(picks), dtype=np.float32)
+        seen = []
+        for rank in range(world):
+            positions, local_clip, times = sharding.route_requests(req_clip, req_time, owner, local, rank)
+            seen += list(positions)
+            for pos, lc in zip(positions, local_clip):
+                clip = int(req_clip[pos])
+                if clip < len(sizes):
+                    assert owner[clip] == rank and local[clip] == lc
+                else:
+                    assert rank == 0 and lc == 0xFFFFFFFF
+        assert sorted(seen) == list(range(len(picks)))
+
+    check()
