@@ -111,6 +111,7 @@ def _lib():
         l.aclb200_decompress_tracks_host.argtypes = [vp, vp, vp, u32, C.POINTER(Options), vp, C.c_size_t]
         l.aclb200_debug_seek.argtypes = [vp, vp, vp, u32, C.POINTER(Options), vp, vp]
         l.aclb200_debug_unpack.argtypes = [vp, vp, vp, u32, C.POINTER(Options), u32, u32, vp, vp]
+        l.aclb200_debug_set_trace.argtypes = [vp, vp, u32, u32]
         l.aclb200_launch_count.argtypes = [vp]
         l.aclb200_launch_count.restype = u64
         _lib_handle = l
@@ -124,7 +125,7 @@ def exported_symbols() -> list[str]:
         "aclb200_last_error", "aclb200_upload_clips", "aclb200_upload_clips_packed", "aclb200_release_clipset",
         "aclb200_clipset_get_info", "aclb200_clipset_get_clip_info", "aclb200_decompress_tracks", "aclb200_decompress_track",
         "aclb200_scalar_decompress_tracks", "aclb200_scalar_decompress_track", "aclb200_decompress_tracks_host",
-        "aclb200_debug_seek", "aclb200_debug_unpack", "aclb200_launch_count",
+        "aclb200_debug_seek", "aclb200_debug_unpack", "aclb200_debug_set_trace", "aclb200_launch_count",
     ]
 
 
@@ -265,6 +266,9 @@ class Context:
     def debug_unpack(self, clipset: ClipSet, d_requests, num_requests: int, options: Options, which: int, max_sub_tracks: int, d_out, stream=None) -> None:
         self._check(_lib().aclb200_debug_unpack(self._handle, clipset._handle, _device_ptr(d_requests), num_requests, C.byref(options),
                                                 which, max_sub_tracks, _device_ptr(d_out), _stream_ptr(stream)))
+
+    def debug_set_trace(self, d_trace, num_blocks: int, num_iterations: int) -> None:
+        self._check(_lib().aclb200_debug_set_trace(self._handle, _device_ptr(d_trace), num_blocks, num_iterations))
 
     # ---- host buffers in, host buffers out (the call the C++ header shim uses) ----
     def decompress_tracks_host(self, clipset: ClipSet, requests: np.ndarray, options: Options, out: np.ndarray) -> np.ndarray:

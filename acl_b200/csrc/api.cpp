@@ -263,6 +263,9 @@ extern "C"
 			{
 				const bool rows_16 = options->output_layout == ACLB200_LAYOUT_QVV48 || clipset->all_tracks_even;
 				pipeline_params.out_bulk = rows_16 && ((uint64_t(reinterpret_cast<uintptr_t>(d_out)) | pipeline_params.pose_stride) & 15) == 0 ? 1u : 0u;
+				pipeline_params.trace = context->d_trace;
+				pipeline_params.trace_blocks = context->trace_blocks;
+				pipeline_params.trace_iterations = context->trace_iterations;
 				acquire_base_poses(clipset, pipeline_params, static_cast<cudaStream_t>(stream));
 				return finish_launch(context, launch_transform_pipeline(pipeline_params, options->math_mode, static_cast<cudaStream_t>(stream)), "decompress_tracks (pipeline)");
 			}
@@ -401,6 +404,16 @@ extern "C"
 		params.debug_max_sub_tracks = max_animated_sub_tracks;
 		cudaSetDevice(context->device);
 		return finish_launch(context, launch_transform_debug_unpack(params, d_out, static_cast<cudaStream_t>(stream)), "debug_unpack");
+	}
+
+	aclb200_status aclb200_debug_set_trace(aclb200_context* context, void* d_trace, uint32_t num_blocks, uint32_t num_iterations)
+	{
+		if (context == nullptr)
+			return ACLB200_ERR_INVALID_ARGUMENT;
+		context->d_trace = static_cast<unsigned long long*>(d_trace);
+		context->trace_blocks = d_trace != nullptr ? num_blocks : 0;
+		context->trace_iterations = d_trace != nullptr ? num_iterations : 0;
+		return ACLB200_OK;
 	}
 
 	uint64_t aclb200_launch_count(const aclb200_context* context)

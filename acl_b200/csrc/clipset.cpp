@@ -490,7 +490,7 @@ namespace aclb200
 						Entry entry = {};
 						uint32_t code, stream_bits;
 						entry.inv_max = 1.0F;
-						entry.extent[0] = entry.extent[1] = entry.extent[2] = 1.0F;
+						entry.extent_x = entry.extent_y = entry.extent_z = 1.0F;
 						if (variable[kind])
 						{
 							const uint32_t stored = format[kind_format_offset[kind] + index];
@@ -528,8 +528,9 @@ namespace aclb200
 								}
 								code = 0;
 								stream_bits = 0;
-								const uint32_t sample[3] = { x, y, z };
-								std::memcpy(entry.min, sample, sizeof(sample));
+								std::memcpy(&entry.min_x, &x, 4);
+								std::memcpy(&entry.min_y, &y, 4);
+								std::memcpy(&entry.min_z, &z, 4);
 								entry.inv_max = 1.0F / 65535.0F;
 							}
 							else if (stored == raw_marker)
@@ -543,11 +544,8 @@ namespace aclb200
 								stream_bits = stored * 3;
 								// unpack_segment_range_data: u8 -> float, times 1 / 255 in float (:157-298; vectors math/vector4_packing.h:781-818)
 								const float n = 1.0F / 255.0F;
-								for (int c = 0; c < 3; ++c)
-								{
-									entry.min[c] = float(r[c]) * n;
-									entry.extent[c] = float(r[3 + c]) * n;
-								}
+								entry.min_x = float(r[0]) * n; entry.min_y = float(r[1]) * n; entry.min_z = float(r[2]) * n;
+								entry.extent_x = float(r[3]) * n; entry.extent_y = float(r[4]) * n; entry.extent_z = float(r[5]) * n;
 								entry.inv_max = inv_max_value(stored);
 							}
 							else

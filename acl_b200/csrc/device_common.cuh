@@ -383,16 +383,23 @@ namespace aclb200
 		// ---------------------------------------------------------------------------------------------------
 		// sub-track decoders
 		// ---------------------------------------------------------------------------------------------------
+		// a = first 16 byte half of an Entry, b = second half (layout.h)
+		__device__ __forceinline__ Entry entry_from(const uint4& a, const uint4& b)
+		{
+			Entry e;
+			e.offset_code = a.x; e.inv_max = __uint_as_float(a.y);
+			e.min_x = __uint_as_float(a.z); e.min_y = __uint_as_float(a.w);
+			e.extent_x = __uint_as_float(b.x); e.extent_y = __uint_as_float(b.y);
+			e.min_z = __uint_as_float(b.z); e.extent_z = __uint_as_float(b.w);
+			return e;
+		}
+
 		__device__ __forceinline__ Entry load_entry(const ReqState& rs, int k, uint32_t slot)
 		{
 			// two arrays of 16 byte halves (layout.h)
 			const uint4* src = reinterpret_cast<const uint4*>(rs.image + rs.entries_off[k]) + slot;
 			const uint4 a = __ldg(src), b = __ldg(src + (rs.num_animated[0] + rs.num_animated[1] + rs.num_animated[2]));
-			Entry e;
-			e.offset_code = a.x; e.inv_max = __uint_as_float(a.y);
-			e.min[0] = __uint_as_float(a.z); e.min[1] = __uint_as_float(a.w); e.min[2] = __uint_as_float(b.x);
-			e.extent[0] = __uint_as_float(b.y); e.extent[1] = __uint_as_float(b.z); e.extent[2] = __uint_as_float(b.w);
-			return e;
+			return entry_from(a, b);
 		}
 
 		// Raw integers of one animated sample: x, y, z (quantised integers or raw float bits), shared by the decode and by the
@@ -408,9 +415,9 @@ namespace aclb200
 			{
 				// constant inside the segment: the 3 x 16 bit sample was gathered from the segment range bytes at upload
 				// (animated_track_cache.transform.h:552-587; unpack_vector3_u48_unsafe, math/vector4_packing.h:628-653)
-				xi = __float_as_uint(e.min[0]);
-				yi = __float_as_uint(e.min[1]);
-				zi = __float_as_uint(e.min[2]);
+				xi = __float_as_uint(e.min_x);
+				yi = __float_as_uint(e.min_y);
+				zi = __float_as_uint(e.min_z);
 			}
 			else if (code & k_entry_raw)
 			{
@@ -470,9 +477,9 @@ namespace aclb200
 			{
 				// unpack_segment_range_data, :157-298: u8 * (1 / 255), done at upload (layout.h Entry)
 				const bool constant_sample = code == 0;		// its min[] holds the sample integers
-				x = fmuladd(x, e.extent[0], constant_sample ? 0.0f : e.min[0]);
-				y = fmuladd(y, e.extent[1], constant_sample ? 0.0f : e.min[1]);
-				z = fmuladd(z, e.extent[2], constant_sample ? 0.0f : e.min[2]);
+				x = fmuladd(x, e.extent_x, constant_sample ? 0.0f : e.min_x);
+				y = fmuladd(y, e.extent_y, constant_sample ? 0.0f : e.min_y);
+				z = fmuladd(z, e.extent_z, constant_sample ? 0.0f : e.min_z);
 			}
 
 			if (!SINGLE || !ignore_clip)
@@ -508,9 +515,9 @@ namespace aclb200
 			if (code != 0 && (rs.clip_flags & k_clip_has_segments))
 			{
 				// unpack_vector3_u24_unsafe min then extent, math/vector4_packing.h:781-818 (converted at upload)
-				x = fmuladd(x, e.extent[0], e.min[0]);
-				y = fmuladd(y, e.extent[1], e.min[1]);
-				z = fmuladd(z, e.extent[2], e.min[2]);
+				x = fmuladd(x, e.extent_x, e.min_x);
+				y = fmuladd(y, e.extent_y, e.min_y);
+				z = fmuladd(z, e.extent_z, e.min_z);
 			}
 			// clip range (:949-958)
 			out[0] = fmuladd(x, clip_extent.x, clip_min.x);

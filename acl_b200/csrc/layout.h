@@ -129,9 +129,12 @@ namespace aclb200
 		float    inv_max;		// 1 / (2^code - 1) (PackedTableEntry::max_value, math/vector4_packing.h:927-929); 1 / 65535 for code 0
 		// code 1..23: the segment range of the sub-track already as floats, u8 * (1 / 255) evaluated in float on the host exactly as
 		// unpack_segment_range_data does (animated_track_cache.transform.h:157-298); code 0: the bit patterns of the three 16 bit
-		// integers of the constant sample sit in min[]; raw: min = 0, extent = 1 (an ignored range still multiplies by 1 and adds 0)
-		float    min[3];
-		float    extent[3];
+		// integers of the constant sample sit in min_*; raw: min = 0, extent = 1 (an ignored range still multiplies by 1 and adds 0).
+		// Field order: (min_x, min_y) and (extent_x, extent_y) each fill an aligned register pair of the 16 byte halves the kernels
+		// load, so the packed f32x2 instructions take them without moves.
+		float    min_x, min_y;
+		float    extent_x, extent_y;
+		float    min_z, extent_z;
 	};
 	static_assert(sizeof(Entry) == 32, "Entry is 32 bytes");
 

@@ -231,6 +231,11 @@ ACLB200_API aclb200_status aclb200_debug_unpack(aclb200_context* context, const 
 	const aclb200_request* d_requests, uint32_t num_requests, const aclb200_options* options, uint32_t which,
 	uint32_t max_animated_sub_tracks, uint32_t* d_out, void* stream);
 
+/* Profiling hook of the pipeline kernel (only builds compiled with -DACLB200_PIPE_TRACE=1 write anything): the first
+ * `num_blocks` blocks record 8 clock64() stamps per batch they decode, for their first `num_iterations` batches, at
+ * d_trace[(block * num_iterations + iteration) * 8 + k] (uint64). NULL switches it off. tools/pipe_trace.py reads it. */
+ACLB200_API aclb200_status aclb200_debug_set_trace(aclb200_context* context, void* d_trace, uint32_t num_blocks, uint32_t num_iterations);
+
 /* Number of kernels launched by this context so far (bench.py reports it as `gpu_launches`). */
 ACLB200_API uint64_t aclb200_launch_count(const aclb200_context* context);
 

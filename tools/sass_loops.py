@@ -1,9 +1,11 @@
-"""Static view of a kernel's SASS loops (development helper): python tools/sass_loops.py <lib.so> <kernel substring>"""
+"""Static view of a kernel's SASS loops (development helper): python tools/sass_loops.py <lib.so> <kernel substring> [max body size] [print]
+Lists every loop (backward branch) smallest first with its opcode mix; `print` dumps the bodies too."""
 import collections, re, subprocess, sys
 lib, pat = sys.argv[1], sys.argv[2]
+limit = int(sys.argv[3]) if len(sys.argv) > 3 else 400
+show = len(sys.argv) > 4
 txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-blocks = txt.split("Function : ")
-for b in blocks[1:]:
+for b in txt.split("Function : ")[1:]:
     name = b.split("\n", 1)[0]
     if pat not in name:
         continue
@@ -13,17 +15,20 @@ for b in blocks[1:]:
         if m:
             ins.append((int(m.group(1), 16), m.group(2).strip()))
     print(name[:110], "static instructions:", len(ins))
-    addr_index = {a: i for i, (a, _) in enumerate(ins)}
+    idx = {a: i for i, (a, _) in enumerate(ins)}
     loops = []
     for i, (a, t) in enumerate(ins):
-        m = re.search(r"\bBRA(?:\.U)?\s+(?:!?U?P\d+,\s*)?`?\(?\.?L?_?x?_?([0-9a-f]+)?\)?|BRA.*?0x([0-9a-f]+)", t)
-        m2 = re.search(r"0x([0-9a-f]+)", t) if "BRA" in t else None
-        if m2:
-            target = int(m2.group(1), 16)
-            if target <= a and target in addr_index:
-                loops.append((addr_index[target], i))
-    for s, e in sorted(loops, key=lambda x: -(x[1] - x[0]))[:8]:
+        if "BRA" in t:
+            m = re.search(r"0x([0-9a-f]+)", t)
+            if m and int(m.group(1), 16) <= a and int(m.group(1), 16) in idx:
+                loops.append((idx[int(m.group(1), 16)], i))
+    for s, e in sorted(loops, key=lambda x: x[1] - x[0]):
         body = ins[s:e + 1]
+        if len(body) < 20 or len(body) > limit:
+            continue
         ops = collections.Counter(re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_.]+)", t).group(2).split(".")[0] for _, t in body)
-        print(f"  loop {ins[s][0]:#x}..{ins[e][0]:#x}: {len(body)} instr  ", ops.most_common(14))
+        print(f"  loop {ins[s][0]:#x}..{ins[e][0]:#x}: {len(body)} instr  ", ops.most_common(16))
+        if show:
+            for a, t in body:
+                print(f"      {a:#06x}  {t}")
     break
