@@ -180,6 +180,11 @@ extern "C"
 		cudaFree(context->d_scratch_out);
 		if (context->host_stream != nullptr)
 			cudaStreamDestroy(context->host_stream);
+		if (context->copy_stream != nullptr)
+			cudaStreamDestroy(context->copy_stream);
+		for (cudaEvent_t event : context->chunk_done)
+			if (event != nullptr)
+				cudaEventDestroy(event);
 		delete context;
 	}
 
@@ -355,27 +360,66 @@ extern "C"
 			return check_cuda(context, error, "decompress_tracks_host: scratch allocation");
 
 		cudaStream_t stream = context->host_stream;
+		if (context->copy_stream == nullptr)
+			error = cudaStreamCreateWithFlags(&context->copy_stream, cudaStreamNonBlocking);
+		for (int i = 0; i < 2 && error == cudaSuccess; ++i)
+			if (context->chunk_done[i] == nullptr)
+				error = cudaEventCreateWithFlags(&context->chunk_done[i], cudaEventDisableTiming);
+		if (error != cudaSuccess)
+			return check_cuda(context, error, "decompress_tracks_host: streams");
+
 		// `skipped` default sub-tracks keep what the caller's buffer held: bring the buffer in first in that case
 		const bool keeps_input = is_transform && (options->default_rotation_mode == ACLB200_DEFAULT_SKIPPED
 			|| options->default_translation_mode == ACLB200_DEFAULT_SKIPPED || options->default_scale_mode == ACLB200_DEFAULT_SKIPPED);
+		// Rows no request writes (clips shorter than the widest one, requests naming a clip outside the set) read as zero. Clearing the
+		// scratch costs a pass over it, so it only happens when such rows can exist.
+		bool needs_clear = !keeps_input && (clipset->info.min_tracks != clipset->info.max_tracks || pose_stride != uint64_t(clipset->info.max_tracks) * bone_stride);
+		if (!keeps_input && !needs_clear)
+			for (uint32_t r = 0; r < num_requests && !needs_clear; ++r)
+				needs_clear = requests[r].clip >= clipset->info.num_clips;
+
 		error = cudaMemcpyAsync(context->d_scratch_requests, requests, needed_requests, cudaMemcpyHostToDevice, stream);
 		if (error == cudaSuccess && keeps_input)
 			error = cudaMemcpyAsync(context->d_scratch_out, out, needed_out, cudaMemcpyHostToDevice, stream);
-		else if (error == cudaSuccess)
-			error = cudaMemsetAsync(context->d_scratch_out, 0, needed_out, stream);	// rows no request writes (shorter clips, invalid requests) read as zero
+		else if (error == cudaSuccess && needs_clear)
+			error = cudaMemsetAsync(context->d_scratch_out, 0, needed_out, stream);
 		if (error != cudaSuccess)
 			return check_cuda(context, error, "decompress_tracks_host: upload");
 
+		// Decode in a few chunks on one stream while the previous chunk's poses cross PCIe on another: the copy is the long pole
+		// (tens of milliseconds per GB against well under a millisecond of decode), so it starts as early as possible and never waits
+		// for the whole batch.
+		const uint32_t num_chunks = num_requests >= 65536 ? 8u : (num_requests >= 4096 ? 2u : 1u);
 		const aclb200_request* d_requests = static_cast<const aclb200_request*>(context->d_scratch_requests);
-		const aclb200_status status = is_transform
-			? aclb200_decompress_tracks(context, clipset, d_requests, num_requests, options, context->d_scratch_out, stream)
-			: aclb200_scalar_decompress_tracks(context, clipset, d_requests, num_requests, options, context->d_scratch_out, stream);
-		if (status != ACLB200_OK)
-			return status;
-
-		error = cudaMemcpyAsync(out, context->d_scratch_out, needed_out, cudaMemcpyDeviceToHost, stream);
-		if (error == cudaSuccess)
-			error = cudaStreamSynchronize(stream);
+		uint8_t* d_out = static_cast<uint8_t*>(context->d_scratch_out);
+		for (uint32_t chunk = 0; chunk < num_chunks; ++chunk)
+		{
+			const uint32_t first = uint32_t(uint64_t(num_requests) * chunk / num_chunks);
+			const uint32_t last = uint32_t(uint64_t(num_requests) * (chunk + 1) / num_chunks);
+			if (first == last)
+				continue;
+			uint8_t* d_chunk = d_out + size_t(first) * pose_stride;
+			const aclb200_status status = is_transform
+				? aclb200_decompress_tracks(context, clipset, d_requests + first, last - first, options, d_chunk, stream)
+				: aclb200_scalar_decompress_tracks(context, clipset, d_requests + first, last - first, options, d_chunk, stream);
+			if (status != ACLB200_OK)
+			{
+				cudaStreamSynchronize(stream);
+				cudaStreamSynchronize(context->copy_stream);
+				return status;
+			}
+			cudaEvent_t done = context->chunk_done[chunk & 1];
+			error = cudaEventRecord(done, stream);
+			if (error == cudaSuccess) error = cudaStreamWaitEvent(context->copy_stream, done, 0);
+			if (error == cudaSuccess)
+				error = cudaMemcpyAsync(static_cast<uint8_t*>(out) + size_t(first) * pose_stride, d_chunk, size_t(last - first) * pose_stride, cudaMemcpyDeviceToHost, context->copy_stream);
+			if (error != cudaSuccess)
+				break;
+		}
+		const cudaError_t sync_decode = cudaStreamSynchronize(stream);
+		const cudaError_t sync_copy = cudaStreamSynchronize(context->copy_stream);
+		if (error == cudaSuccess) error = sync_decode;
+		if (error == cudaSuccess) error = sync_copy;
 		return check_cuda(context, error, "decompress_tracks_host: download");
 	}
 

@@ -10,10 +10,16 @@
 // in the same order as the reference's decoder, so nothing about the results changes.
 #include "context.h"
 
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <functional>
 #include <limits>
+#include <new>
+#include <thread>
+#if defined(__linux__)
+#include <sched.h>
+#endif
 
 namespace aclb200
 {
@@ -52,15 +58,20 @@ namespace aclb200
 			return 1.0F / float((1u << num_bits) - 1u);
 		}
 
+		struct image_too_large {};
+
 		// Growable clip image with 16 byte aligned sections
 		struct image_builder
 		{
 			std::vector<uint8_t>& bytes;
 			size_t base;
 			explicit image_builder(std::vector<uint8_t>& bytes_) : bytes(bytes_), base(bytes_.size()) {}
+			// image offsets are 32 bit: a clip whose image would pass 4 GiB is refused (image_too_large, caught by build_clipset), never wrapped
 			uint32_t reserve(size_t size)
 			{
 				const size_t offset = align_up64(bytes.size() - base, k_section_alignment);
+				if (offset + size > 0xFFFFFFF0ull)
+					throw image_too_large();
 				bytes.resize(base + offset + size, 0);
 				return uint32_t(offset);
 			}
@@ -255,6 +266,13 @@ namespace aclb200
 			const uint32_t num_animated_total = num_animated[0] + num_animated[1] + num_animated[2];
 			const uint32_t num_kinds = has_scale ? 3u : 2u;
 
+			// the per segment format / range tables are indexed by sub-track: the header's count must cover every variable sub-track
+			// (compress.transform.impl.h:435 stores exactly this sum, rotations padded to groups of 4)
+			{
+				const uint64_t expected_variable = uint64_t(variable[0] ? padded_rotations : 0u) + (variable[1] ? num_animated[1] : 0u) + (variable[2] ? num_animated[2] : 0u);
+				if (expected_variable > num_variable)
+					return "num_animated_variable_sub_tracks is smaller than the variable sub-track counts";
+			}
 			if (!in_bounds(segment_headers_offset, uint64_t(segment_header_size) * num_segments))
 				return "segment headers out of bounds";
 			if (!in_bounds(sub_track_types_offset, uint64_t(num_entries) * 4 * num_kinds))
@@ -591,6 +609,40 @@ namespace aclb200
 		return set_error(context, status, std::string(what) + ": " + cudaGetErrorString(error));
 	}
 
+	namespace
+	{
+		// host threads the transcode may use: the scheduler affinity of the calling thread, at most 32
+		uint32_t transcode_threads(uint32_t num_clips)
+		{
+			uint32_t threads = std::thread::hardware_concurrency();
+#if defined(__linux__)
+			cpu_set_t set;
+			if (sched_getaffinity(0, sizeof(set), &set) == 0)
+				threads = uint32_t(CPU_COUNT(&set));
+#endif
+			if (threads > 32) threads = 32;
+			if (threads > num_clips / 64) threads = num_clips / 64;		// not worth a thread for a handful of clips
+			return threads == 0 ? 1 : threads;
+		}
+
+		// runs job(thread_index, first, last) over [0, count) split into contiguous ranges, on `threads` threads
+		template<class Job>
+		void parallel_ranges(uint32_t count, uint32_t threads, const Job& job)
+		{
+			if (threads <= 1)
+			{
+				job(0u, 0u, count);
+				return;
+			}
+			std::vector<std::thread> pool;
+			pool.reserve(threads);
+			for (uint32_t t = 0; t < threads; ++t)
+				pool.emplace_back([&, t]() { job(t, uint32_t(uint64_t(count) * t / threads), uint32_t(uint64_t(count) * (t + 1) / threads)); });
+			for (std::thread& thread : pool)
+				thread.join();
+		}
+	}
+
 	aclb200_status build_clipset(aclb200_context* context, const std::function<const uint8_t*(uint32_t)>& get_blob, const uint32_t* sizes,
 		uint32_t num_clips, bool check_hash, aclb200_clipset** out_clipset, uint32_t* out_failed_clip)
 	{
@@ -598,100 +650,177 @@ namespace aclb200
 			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "upload_clips: null argument or empty clip list");
 		*out_clipset = nullptr;
 
-		aclb200_clipset* set = new aclb200_clipset();
-		set->device = context->device;
-		set->host_clips.resize(num_clips);
-		set->host_looping.resize(num_clips);
-
-		auto fail = [&](aclb200_status status, const std::string& message, uint32_t clip)
+		aclb200_clipset* set = nullptr;
+		try
 		{
-			if (out_failed_clip != nullptr)
-				*out_failed_clip = clip;
-			delete set;
-			return set_error(context, status, message);
-		};
+			set = new aclb200_clipset();
+			set->device = context->device;
+			set->host_clips.resize(num_clips);
+			set->host_looping.resize(num_clips);
 
-		// Transcode in chunks so that a multi-GB clip set never needs a second full host copy: the clip images of a chunk are
-		// built in a staging vector and copied to the device when it fills up. Pass 1 only validates and sizes the device buffer.
-		const size_t staging_capacity = size_t(128) << 20;
-		std::vector<uint8_t> staging;
-		parse_result parsed;
-		uint64_t blob_bytes = 0, total_image_bytes = 0;
-		uint32_t set_track_type = 0xFFFFFFFFu;
-		uint32_t max_tracks = 0, min_tracks = std::numeric_limits<uint32_t>::max();
-
-		for (uint32_t clip = 0; clip < num_clips; ++clip)
-		{
-			bool unsupported = false;
-			staging.clear();
-			const std::string error = transcode_clip(get_blob(clip), sizes[clip], check_hash, staging, parsed, unsupported);
-			if (!error.empty())
-				return fail(unsupported ? ACLB200_ERR_UNSUPPORTED : ACLB200_ERR_INVALID_CLIP, "clip " + std::to_string(clip) + ": " + error, clip);
-			if (set_track_type == 0xFFFFFFFFu)
-				set_track_type = parsed.track_type;
-			else if (set_track_type != parsed.track_type)
-				return fail(ACLB200_ERR_UNSUPPORTED, "clip " + std::to_string(clip) + ": a clip set holds a single track type", clip);
-
-			ClipDesc& desc = set->host_clips[clip];
-			desc = parsed.desc;
-			desc.data_offset = total_image_bytes;
-			total_image_bytes += align_up64(desc.image_size, k_section_alignment);
-			blob_bytes += desc.size;
-			set->host_looping[clip] = parsed.looping_policy;
-			max_tracks = desc.num_tracks > max_tracks ? desc.num_tracks : max_tracks;
-			if (desc.num_tracks % 2 != 0)
-				set->all_tracks_even = false;
-			min_tracks = desc.num_tracks < min_tracks ? desc.num_tracks : min_tracks;
-			if (parsed.track_type == k_track_qvvf)
+			auto fail = [&](aclb200_status status, const std::string& message, uint32_t clip)
 			{
-				for (int k = 0; k < 3; ++k)
-					set->max_animated[k] = desc.num_animated[k] > set->max_animated[k] ? desc.num_animated[k] : set->max_animated[k];
-				set->max_animated_total = desc.num_animated_total > set->max_animated_total ? desc.num_animated_total : set->max_animated_total;
-				set->max_key_frame_bytes = parsed.max_key_frame_bytes > set->max_key_frame_bytes ? parsed.max_key_frame_bytes : set->max_key_frame_bytes;
-			}
-		}
-		total_image_bytes += k_stream_tail;
+				if (out_failed_clip != nullptr)
+					*out_failed_clip = clip;
+				delete set;
+				return set_error(context, status, message);
+			};
 
-		set->info.num_clips = num_clips;
-		set->info.track_type = set_track_type;
-		set->info.max_tracks = max_tracks;
-		set->info.min_tracks = min_tracks;
-		set->info.blob_bytes = blob_bytes;
-		set->info.index_bytes = total_image_bytes;
-
-		// pass 2: device allocation, transcode again chunk by chunk and copy
-		cudaError_t error = cudaSetDevice(context->device);
-		if (error == cudaSuccess) error = cudaMalloc(reinterpret_cast<void**>(&set->d_data), total_image_bytes);
-		if (error == cudaSuccess) error = cudaMalloc(reinterpret_cast<void**>(&set->d_clips), sizeof(ClipDesc) * size_t(num_clips));
-		if (error == cudaSuccess) error = cudaMemset(set->d_data + (total_image_bytes - k_stream_tail), 0, k_stream_tail);
-		if (error == cudaSuccess)
-		{
-			staging.clear();
-			uint64_t staging_base = 0;
-			for (uint32_t clip = 0; clip < num_clips && error == cudaSuccess; ++clip)
+			// Pass 1 (host threads, clips split into contiguous ranges): validate every clip and measure its image. Nothing is kept but
+			// the descriptors: a multi-GB clip set never needs a second full host copy.
+			const uint32_t threads = transcode_threads(num_clips);
+			struct range_result
 			{
+				uint32_t failed_clip = 0xFFFFFFFFu;
 				bool unsupported = false;
-				transcode_clip(get_blob(clip), sizes[clip], false, staging, parsed, unsupported);
-				staging.resize(align_up64(staging.size(), k_section_alignment), 0);
-				if (staging.size() >= staging_capacity || clip + 1 == num_clips)
+				std::string error;
+				uint32_t max_key_frame_bytes = 0;
+			};
+			std::vector<range_result> results(threads);
+			std::vector<uint32_t> track_types(num_clips);
+			parallel_ranges(num_clips, threads, [&](uint32_t t, uint32_t first, uint32_t last)
+			{
+				std::vector<uint8_t> staging;
+				parse_result parsed;
+				range_result& result = results[t];
+				for (uint32_t clip = first; clip < last; ++clip)
 				{
-					error = cudaMemcpy(set->d_data + staging_base, staging.data(), staging.size(), cudaMemcpyHostToDevice);
-					staging_base += staging.size();
+					bool unsupported = false;
 					staging.clear();
+					std::string error;
+					try
+					{
+						error = transcode_clip(get_blob(clip), sizes[clip], check_hash, staging, parsed, unsupported);
+					}
+					catch (const image_too_large&)
+					{
+						error = "the clip image would pass 4 GiB";
+						unsupported = true;
+					}
+					catch (const std::bad_alloc&)
+					{
+						error = "out of host memory";
+						unsupported = true;
+					}
+					if (!error.empty())
+					{
+						result.failed_clip = clip;
+						result.unsupported = unsupported;
+						result.error = error;
+						return;
+					}
+					set->host_clips[clip] = parsed.desc;
+					set->host_looping[clip] = parsed.looping_policy;
+					track_types[clip] = parsed.track_type;
+					result.max_key_frame_bytes = parsed.max_key_frame_bytes > result.max_key_frame_bytes ? parsed.max_key_frame_bytes : result.max_key_frame_bytes;
+				}
+			});
+			for (const range_result& result : results)		// ranges are in clip order: the first failure is the lowest clip
+				if (result.failed_clip != 0xFFFFFFFFu)
+					return fail(result.unsupported ? ACLB200_ERR_UNSUPPORTED : ACLB200_ERR_INVALID_CLIP,
+						"clip " + std::to_string(result.failed_clip) + ": " + result.error, result.failed_clip);
+
+			uint64_t blob_bytes = 0, total_image_bytes = 0;
+			const uint32_t set_track_type = track_types[0];
+			uint32_t max_tracks = 0, min_tracks = std::numeric_limits<uint32_t>::max();
+			for (uint32_t clip = 0; clip < num_clips; ++clip)
+			{
+				if (track_types[clip] != set_track_type)
+					return fail(ACLB200_ERR_UNSUPPORTED, "clip " + std::to_string(clip) + ": a clip set holds a single track type", clip);
+				ClipDesc& desc = set->host_clips[clip];
+				desc.data_offset = total_image_bytes;
+				total_image_bytes += align_up64(desc.image_size, k_section_alignment);
+				blob_bytes += desc.size;
+				max_tracks = desc.num_tracks > max_tracks ? desc.num_tracks : max_tracks;
+				if (desc.num_tracks % 2 != 0)
+					set->all_tracks_even = false;
+				min_tracks = desc.num_tracks < min_tracks ? desc.num_tracks : min_tracks;
+				if (set_track_type == k_track_qvvf)
+				{
+					for (int k = 0; k < 3; ++k)
+						set->max_animated[k] = desc.num_animated[k] > set->max_animated[k] ? desc.num_animated[k] : set->max_animated[k];
+					set->max_animated_total = desc.num_animated_total > set->max_animated_total ? desc.num_animated_total : set->max_animated_total;
 				}
 			}
-		}
-		if (error == cudaSuccess) error = cudaMemcpy(set->d_clips, set->host_clips.data(), sizeof(ClipDesc) * size_t(num_clips), cudaMemcpyHostToDevice);
-		if (error != cudaSuccess)
-		{
-			const aclb200_status status = check_cuda(context, error, "upload_clips");
-			cudaFree(set->d_data);
-			cudaFree(set->d_clips);
-			delete set;
-			return status;
-		}
+			if (set_track_type == k_track_qvvf)
+				for (const range_result& result : results)
+					set->max_key_frame_bytes = result.max_key_frame_bytes > set->max_key_frame_bytes ? result.max_key_frame_bytes : set->max_key_frame_bytes;
+			total_image_bytes += k_stream_tail;
 
-		*out_clipset = set;
-		return ACLB200_OK;
+			set->info.num_clips = num_clips;
+			set->info.track_type = set_track_type;
+			set->info.max_tracks = max_tracks;
+			set->info.min_tracks = min_tracks;
+			set->info.blob_bytes = blob_bytes;
+			set->info.index_bytes = total_image_bytes;
+
+			// Pass 2: device allocation, then chunk by chunk: the host threads transcode the chunk's clips straight to their final
+			// offsets inside a staging buffer, one copy brings it to the device.
+			cudaError_t error = cudaSetDevice(context->device);
+			if (error == cudaSuccess) error = cudaMalloc(reinterpret_cast<void**>(&set->d_data), total_image_bytes);
+			if (error == cudaSuccess) error = cudaMalloc(reinterpret_cast<void**>(&set->d_clips), sizeof(ClipDesc) * size_t(num_clips));
+			if (error == cudaSuccess) error = cudaMemset(set->d_data + (total_image_bytes - k_stream_tail), 0, k_stream_tail);
+			const uint64_t staging_capacity = uint64_t(256) << 20;
+			std::vector<uint8_t> staging;
+			for (uint32_t chunk_first = 0; chunk_first < num_clips && error == cudaSuccess; )
+			{
+				uint32_t chunk_last = chunk_first;
+				const uint64_t chunk_base = set->host_clips[chunk_first].data_offset;
+				uint64_t chunk_bytes = 0;
+				while (chunk_last < num_clips && (chunk_last == chunk_first || chunk_bytes + align_up64(set->host_clips[chunk_last].image_size, k_section_alignment) <= staging_capacity))
+				{
+					chunk_bytes += align_up64(set->host_clips[chunk_last].image_size, k_section_alignment);
+					++chunk_last;
+				}
+				staging.assign(size_t(chunk_bytes), 0);
+				std::atomic<bool> out_of_memory(false);
+				parallel_ranges(chunk_last - chunk_first, threads, [&](uint32_t, uint32_t first, uint32_t last)
+				{
+					try
+					{
+						std::vector<uint8_t> image;
+						parse_result parsed;
+						for (uint32_t clip = chunk_first + first; clip < chunk_first + last; ++clip)
+						{
+							bool unsupported = false;
+							image.clear();
+							transcode_clip(get_blob(clip), sizes[clip], false, image, parsed, unsupported);		// validated by pass 1
+							std::memcpy(staging.data() + (set->host_clips[clip].data_offset - chunk_base), image.data(), image.size());
+						}
+					}
+					catch (...)		// an exception may not leave a thread
+					{
+						out_of_memory.store(true);
+					}
+				});
+				if (out_of_memory.load())
+					throw std::bad_alloc();
+				error = cudaMemcpy(set->d_data + chunk_base, staging.data(), size_t(chunk_bytes), cudaMemcpyHostToDevice);
+				chunk_first = chunk_last;
+			}
+			if (error == cudaSuccess) error = cudaMemcpy(set->d_clips, set->host_clips.data(), sizeof(ClipDesc) * size_t(num_clips), cudaMemcpyHostToDevice);
+			if (error != cudaSuccess)
+			{
+				const aclb200_status status = check_cuda(context, error, "upload_clips");
+				cudaFree(set->d_data);
+				cudaFree(set->d_clips);
+				delete set;
+				return status;
+			}
+
+			*out_clipset = set;
+			return ACLB200_OK;
+		}
+		catch (const std::exception&)
+		{
+			// (std::bad_alloc, std::system_error of a thread that could not start) nothing may unwind through the extern "C" boundary
+			if (set != nullptr)
+			{
+				cudaFree(set->d_data);
+				cudaFree(set->d_clips);
+				delete set;
+			}
+			return set_error(context, ACLB200_ERR_OUT_OF_MEMORY, "upload_clips: out of host memory");
+		}
 	}
 }

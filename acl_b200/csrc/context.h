@@ -25,6 +25,8 @@ struct aclb200_context
 	void* d_scratch_out = nullptr;
 	size_t scratch_out_bytes = 0;
 	cudaStream_t host_stream = nullptr;
+	cudaStream_t copy_stream = nullptr;			// device -> host copies of the host-buffer call overlap the next chunk's decode
+	cudaEvent_t chunk_done[2] = { nullptr, nullptr };
 
 	// aclb200_debug_set_trace
 	unsigned long long* d_trace = nullptr;

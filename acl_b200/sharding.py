@@ -18,6 +18,10 @@ def partition_clips(sizes, world: int):
     n = len(sizes)
     if world <= 0:
         raise ValueError("world must be positive")
+    if n < world:
+        # a rank without clips cannot build a clip set (aclb200_upload_clips refuses an empty list) and would leave the others
+        # waiting in the job's collectives: refuse up front
+        raise ValueError(f"{n} clips cannot be sharded over {world} ranks: every rank needs at least one clip")
     cumulative = np.concatenate([[0], np.cumsum(sizes)])
     total = int(cumulative[-1])
     cuts = [0]
@@ -26,7 +30,8 @@ def partition_clips(sizes, world: int):
         cut = int(np.searchsorted(cumulative, target, side="left"))
         if cut > 0 and target - cumulative[cut - 1] < cumulative[min(cut, n)] - target:
             cut -= 1  # the boundary before is closer to the ideal split
-        cut = min(max(cut, cuts[-1]), n)
+        # every shard keeps at least one clip, also when one huge clip swallows several ideal cut points
+        cut = min(max(cut, cuts[-1] + 1), n - (world - r))
         cuts.append(cut)
     cuts.append(n)
     owner = np.zeros(n, dtype=np.uint32)
@@ -50,6 +55,42 @@ def route_requests(req_clip, req_time, owner, local_index, rank: int):
     mine = np.nonzero(request_owner == rank)[0]
     local = np.where(valid[mine], local_index[np.minimum(req_clip[mine], max(len(owner) - 1, 0))] if len(owner) else 0, np.uint32(0xFFFFFFFF))
     return mine, local.astype(np.uint32), req_time[mine]
+
+
+def exchange_plan(generated_bounds, owner_bounds, sizes):
+    """Bytes every rank sends to every other rank when clips generated (or loaded) by contiguous ranges `generated_bounds` move to
+    the owners `owner_bounds` picked by partition_clips: plan[src][dst] = (first clip, last clip + 1, bytes). Both partitions are
+    contiguous and cover the same clip list, so what src holds for dst is one contiguous run (possibly empty)."""
+    sizes = np.asarray(sizes, dtype=np.int64)
+    cumulative = np.concatenate([[0], np.cumsum(sizes)])
+    plan = []
+    for g_lo, g_hi in generated_bounds:
+        row = []
+        for o_lo, o_hi in owner_bounds:
+            lo, hi = max(g_lo, o_lo), min(g_hi, o_hi)
+            if lo >= hi:
+                lo = hi = g_lo
+            row.append((int(lo), int(hi), int(cumulative[hi] - cumulative[lo])))
+        plan.append(row)
+    return plan
+
+
+def redistribute_clips(local_bytes, rank: int, plan, device=None):
+    """The batch split over the interconnect: every rank hands the compressed clips it holds to their owners with ONE
+    all_to_all (NCCL over NVLink on GPUs, gloo in the CPU tests). `local_bytes`: uint8 tensor, this rank's clips back to back in
+    clip order (no padding). Returns the uint8 tensor of the clips this rank owns, in clip order."""
+    import torch
+    import torch.distributed as dist
+    world = len(plan)
+    send_splits = [plan[rank][dst][2] for dst in range(world)]
+    recv_splits = [plan[src][rank][2] for src in range(world)]
+    assert int(local_bytes.numel()) == sum(send_splits), "local_bytes must hold exactly the clips of this rank's generated range"
+    received = torch.empty(sum(recv_splits), dtype=torch.uint8, device=local_bytes.device if device is None else device)
+    if world == 1:
+        received.copy_(local_bytes)
+        return received
+    dist.all_to_all_single(received, local_bytes, output_split_sizes=recv_splits, input_split_sizes=send_splits)
+    return received
 
 
 def scatter_results(num_requests: int, row_shape, positions_per_rank, rows_per_rank, dtype=np.float32):

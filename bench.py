@@ -33,6 +33,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+ROUND = 2       # profiles/traffic_*.json of another round are reported as stale
 
 WORKLOADS = {
     # name: (kind, clips per GPU, bones, samples, description)
@@ -319,6 +320,78 @@ def bounded_sample(w, threads: int, seconds: float = 4.0) -> int:
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank: int) -> dict:
+    """Pins this rank's host threads to the CPUs of its GPU's NUMA node BEFORE any pinned host buffer is allocated (first touch then
+    places the pages next to the GPU's PCIe root). Without it the ranks of an 8 GPU box share one node's memory controllers and
+    the D2H copies of the e2e path collapse (round 1: 0.54 G bone-poses/s per GPU at N=8 against 1.32 alone)."""
+    info = {"numa_node": None, "cpus": None}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(visible.split(",")[local_rank]) if visible and visible.replace(",", "").isdigit() else local_rank
+        bus_id = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus_id = (bus_id.decode() if isinstance(bus_id, bytes) else bus_id).lower()
+        if len(bus_id.split(":")[0]) == 8:
+            bus_id = bus_id[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus_id}/numa_node").read())
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info = {"numa_node": node, "cpus": len(allowed)}
+    except Exception as error:      # no NVML / sysfs: keep the default placement, say so
+        info["error"] = str(error)[:80]
+    return info
+
+
+def workload_config(args, w, world: int, num_requests: int, pose_bytes: int, blob_bytes: int) -> dict:
+    """The `config` both arms print (the driver compares them key for key)."""
+    is_transform = w["kind"] == "transform"
+    return {"workload": w["description"], "clips": "distinct" if w["distinct"] else "replicated", "clips_per_gpu": w["num_clips"],
+            "requests_per_step_per_gpu": num_requests, "bones": w["num_tracks"], "layout": args.layout,
+            "l2": f"inputs larger than L2: {blob_bytes / 1e6:.0f} MB compressed + {num_requests * pose_bytes / 1e6:.0f} MB of poses per step vs 126 MB L2",
+            "math": MATH_DESCRIPTION[args.math if is_transform else "exact"], "parallelism": f"clip-sharded x{world}, no data-path collective"}
+
+
+def time_launches(torch, launch, stream, steps: int, warmup: int, barrier, sampler=None):
+    """W untimed + K timed launches bracketed by barrier + synchronize; returns (elapsed ms of the K steps, median launch ms)."""
+    for _ in range(warmup):
+        launch()
+    barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    per_launch = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    host_begin = time.perf_counter()
+    start.record(stream)
+    for a, b in per_launch:
+        a.record(stream)
+        launch()
+        b.record(stream)
+    stop.record(stream)
+    barrier()
+    if sampler is not None:
+        sampler.mark(host_begin, time.perf_counter())
+    return start.elapsed_time(stop), float(np.median([a.elapsed_time(b) for a, b in per_launch]))
+
+
+def measured_traffic(workload: str):
+    """DRAM bytes per launch of the dominant kernel from THIS round's ncu --set full capture (profiles/traffic_<workload>.json, written
+    by tools/ncu_summary.py next to the summary it came from); a file of another round is reported as stale, never silently."""
+    path = os.path.join(ROOT, "profiles", f"traffic_{workload}.json")
+    if not os.path.exists(path):
+        return None, "no ncu capture of this workload"
+    d = json.load(open(path))
+    if d.get("round") != ROUND:
+        return None, f"stale: captured in round {d.get('round', 1)} ({d.get('kernel', '?')}), not re-measured"
+    return d.get("dram_bytes_per_launch"), d.get("source", "ncu --set full")
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -328,12 +401,14 @@ def main() -> None:
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--clips", type=int, default=None, help="override the number of clips per GPU (debugging)")
     ap.add_argument("--layout", default="qvv40", choices=["qvv40", "qvv48"])
-    ap.add_argument("--math", default="fast", choices=["fast", "exact"],
-                    help="fast: hardware sqrt/rsqrt + fused multiply-adds on rotations (<= 1e-5 of the reference, the north star's float gate; "
-                         "translations / scales and every integer stage stay bit-exact); exact: bit-identical to the reference. The other mode is timed too and reported next to it.")
+    ap.add_argument("--math", default="exact", choices=["exact", "fast"],
+                    help="exact (default, the API default and the bit-exact contract): bit-identical to the reference. fast: hardware sqrt/rsqrt + fused "
+                         "multiply-adds on rotations (<= 1e-5 of the reference, the north star's float gate; translations / scales and every integer "
+                         "stage stay bit-exact). The other mode is timed too and reported next to it.")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--gather", action="store_true", help="N > 1: also time decode + NCCL all-gather of the poses (SURVEY 8e, optional consumer-side gather)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra blocks (other workloads at N = 1, the routed C5 job at N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -349,23 +424,27 @@ def main() -> None:
         from oracle import ref
         w = make_workload(args.workload, 0, args.clips)
         blobs = host_blobs(w)
-        threads = ref.lib().aclref_hardware_threads() if ref.available() else 1
+        threads = ref.usable_threads() if ref.available() else 1
         sample = bounded_sample(w, threads)
         for _ in range(args.warmup):
             cpu_reference_pass(w, blobs, sample, threads, 1)
-        # the pass times itself between "every thread is ready" and "every thread has joined" (oracle/ref_tool.cpp): thread start-up
-        # and the per-clip context initialisation are not charged to the reference
+        # the pass times itself between "every thread is ready" and "every thread has joined" (oracle/ref_tool.cpp): thread start-up is not
+        # charged to the reference; a thread's context stays bound to its clip and is re-initialised only when the clip changes
         elapsed = 0.0
         for _ in range(args.steps):
             elapsed += cpu_reference_pass(w, blobs, sample, threads, 1)
         units = sample * w["num_tracks"]
         value = units * args.steps / elapsed
+        single = sample_single_thread(w, blobs)
+        bone_bytes = (40 if args.layout == "qvv40" else 48) if w["kind"] == "transform" else 4
         print(json.dumps({
             "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": w["description"], "clips": "distinct" if w["distinct"] else "replicated"},
-            "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "reference",
-                             "sample": f"{sample} of {len(w['req_clip'])} requests per step, acl::decompression_context<benchmark settings> on {threads} host threads"},
+            "data": "synthetic",
+            "config": workload_config(args, w, 1, len(w["req_clip"]), w["num_tracks"] * bone_bytes, int(w["sizes"].astype(np.int64).sum())),
+            "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "reference", "single_thread_value": single,
+                             "sample": f"{sample} of {len(w['req_clip'])} requests per step, acl::decompression_context<benchmark settings> (one context per clip, "
+                                       f"re-seek per request) on {threads} host threads (affinity / cgroup quota; hardware_concurrency = {os.cpu_count()})"},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return
@@ -376,6 +455,7 @@ def main() -> None:
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     distributed = world > 1
     if distributed:
         import torch.distributed as dist
@@ -384,7 +464,9 @@ def main() -> None:
     w = make_workload(args.workload, rank, args.clips, world)
     is_transform = w["kind"] == "transform"
     ctx = ab.Context(local_rank)
+    upload_begin = time.perf_counter()
     clipset = ctx.upload_packed(w["buffer"], w["offsets"], w["sizes"])
+    upload_seconds = time.perf_counter() - upload_begin
     requests = ab.make_requests(w["req_clip"], w["req_time"])
     num_requests = len(requests)
     layout = ab.LAYOUT_QVV40 if args.layout == "qvv40" else ab.LAYOUT_QVV48
@@ -410,91 +492,75 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()             # before the warm-up: NVML initialisation must not eat the (milliseconds long) timed region
-    for _ in range(args.warmup):
-        launch()
-    barrier()
-    launches_before = ctx.launch_count
-    start = torch.cuda.Event(enable_timing=True)
-    stop = torch.cuda.Event(enable_timing=True)
-    per_launch = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    host_begin = time.perf_counter()
-    start.record(stream)
-    for a, b in per_launch:
-        a.record(stream)
-        launch()
-        b.record(stream)
-    stop.record(stream)
-    barrier()
-    sampler.mark(host_begin, time.perf_counter())
-    clocks = sampler.stop()
-    gpu_launches = ctx.launch_count - launches_before
-    elapsed_ms = start.elapsed_time(stop)
-    kernel_ms = float(np.median([a.elapsed_time(b) for a, b in per_launch]))     # median launch, CUDA events on the launch stream
     from acl_b200.sharding import JobReducer
     reducer = JobReducer(device="cuda")
-    elapsed_ms = reducer.max(elapsed_ms)                                # slowest rank
+    sampler = ClockSampler(local_rank)
+    sampler.start()             # before the warm-up: NVML initialisation must not eat the (milliseconds long) timed region
+    launches_before = ctx.launch_count
+    rank_ms, kernel_ms = time_launches(torch, launch, stream, args.steps, args.warmup, barrier, sampler)
+    clocks = sampler.stop()
+    gpu_launches = ctx.launch_count - launches_before - args.warmup
+    elapsed_ms = reducer.max(rank_ms)                                   # slowest rank
     value = reducer.sum(units_per_step * args.steps) / (elapsed_ms * 1e-3)   # every rank's units
+    per_rank_ms = [rank_ms / args.steps]
+    if distributed:
+        gathered_ms = [None] * world
+        dist.all_gather_object(gathered_ms, rank_ms / args.steps)
+        per_rank_ms = [float(v) for v in gathered_ms]
 
     # ---- the other arithmetic mode, same launches, reported next to the headline ----
     other_math = None
     if is_transform:
         other_mode = ab.MATH_EXACT if math_mode == ab.MATH_FAST else ab.MATH_FAST
         other_options = ab.Options(output_layout=layout, math_mode=other_mode)
-        for _ in range(args.warmup):
-            ctx.decompress_tracks(clipset, d_requests, num_requests, other_options, d_out, stream)
-        barrier()
-        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        o0.record(stream)
-        for _ in range(args.steps):
-            ctx.decompress_tracks(clipset, d_requests, num_requests, other_options, d_out, stream)
-        o1.record(stream)
-        barrier()
-        other_ms = reducer.max(o0.elapsed_time(o1))
+        other_ms, other_kernel_ms = time_launches(torch, lambda: ctx.decompress_tracks(clipset, d_requests, num_requests, other_options, d_out, stream),
+                                                  stream, args.steps, args.warmup, barrier)
+        other_ms = reducer.max(other_ms)
         other_math = {"math": "exact" if other_mode == ab.MATH_EXACT else "fast", "value": reducer.sum(units_per_step * args.steps) / (other_ms * 1e-3),
-                      "unit": unit, "ms_per_step": other_ms / args.steps}
+                      "unit": unit, "ms_per_step": other_ms / args.steps, "kernel_ms": other_kernel_ms}
 
     # ---- optional: every rank ends up with every pose (one NCCL all-gather after the decode; not part of the decode path) ----
     gather = None
     if distributed and args.gather:
         gathered = torch.empty(world * d_out.numel(), dtype=torch.uint8, device="cuda")
-        for _ in range(2):
+
+        def decode_and_gather():
             launch()
             dist.all_gather_into_tensor(gathered, d_out)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record(stream)
-        for _ in range(args.steps):
-            launch()
-            dist.all_gather_into_tensor(gathered, d_out)
-        g1.record(stream)
-        barrier()
-        gather_ms = reducer.max(g0.elapsed_time(g1))
+        gather_ms, _ = time_launches(torch, decode_and_gather, stream, args.steps, 2, barrier)
+        gather_ms = reducer.max(gather_ms)
         gather = {"value": reducer.sum(units_per_step * args.steps) / (gather_ms * 1e-3), "unit": unit,
                   "bytes_gathered_per_step_per_gpu": int(world * d_out.numel()), "collective": "ncclAllGather of the pose buffers"}
         del gathered
 
-    # ---- e2e: host buffers through aclb200_decompress_tracks_host ----
+    # ---- e2e: host buffers through aclb200_decompress_tracks_host (H2D of the requests, decode, D2H of every pose, all inside the timed region) ----
     e2e = None
     if not args.no_e2e:
         h_requests = torch.from_numpy(requests.view(np.uint8).copy()).pin_memory()
         h_out = torch.empty(num_requests * pose_bytes, dtype=torch.uint8).pin_memory()
         req_np = h_requests.numpy().view(ab.api.REQUEST_DTYPE)
         out_np = h_out.numpy()
-        e2e_steps = max(2, min(args.steps, 5))
-        ctx.decompress_tracks_host(clipset, req_np, options, out_np)     # warm-up (allocates the device scratch)
+        e2e_steps = max(args.steps, 2)
+        for _ in range(2):
+            ctx.decompress_tracks_host(clipset, req_np, options, out_np)     # warm-up (allocates the device scratch)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             ctx.decompress_tracks_host(clipset, req_np, options, out_np)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
+        per_rank_gbs = num_requests * pose_bytes * e2e_steps / e2e_s / 1e9
         e2e_s = reducer.max(e2e_s)
         e2e = {"value": reducer.sum(units_per_step * e2e_steps) / e2e_s, "unit": unit, "h2d_bytes_per_step": int(requests.nbytes),
-               "d2h_bytes_per_step": int(num_requests * pose_bytes), "steps": e2e_steps}
+               "d2h_bytes_per_step": int(num_requests * pose_bytes), "steps": e2e_steps, "d2h_gbs_this_rank": per_rank_gbs, "host_numa": numa,
+               "note": "PCIe bound: every pose crosses to the host (at N = 1 about 1.3-1.4 G bone-poses/s whatever the kernel does); "
+                       "device-resident consumers are the use case"}
         del h_out
+
+    # ---- N > 1: BASELINE.json configs[4] as ONE routed job ----
+    c5_sharded = None
+    if distributed and not args.no_extra:
+        c5_sharded = routed_c5_job(args, torch, dist, ab, ctx, rank, local_rank, world, reducer, barrier, layout)
 
     if rank != 0:
         if distributed:
@@ -509,14 +575,11 @@ def main() -> None:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     written_per_step = alg["out_bytes"] * bone_bytes // 40 if is_transform else alg["out_bytes"]
     achieved = (alg["in_bytes"] + alg["out_bytes"]) / (kernel_ms * 1e-3) / 1e9
-    traffic = None
-    traffic_path = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
-    if os.path.exists(traffic_path):
-        traffic = json.load(open(traffic_path)).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "transform_tracks_pipeline_kernel" if is_transform else "scalar_decompress_tracks_kernel",
+    traffic, traffic_source = measured_traffic(args.workload)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source,
+                "kernel": "transform_tracks_pipeline_kernel" if is_transform else "scalar_tracks_pipeline_kernel",
                 "kernel_ms": kernel_ms, "algorithmic_bytes_in": alg["in_bytes"], "algorithmic_bytes_out": alg["out_bytes"],
-                "bytes_written": int(written_per_step), "peak_source": peak_src}
+                "bytes_written": int(written_per_step), "peak_source": peak_src, "math": args.math if is_transform else "exact"}
 
     # ---- CPU baseline (reported, not the target) ----
     cpu_baseline = None
@@ -524,11 +587,13 @@ def main() -> None:
         from oracle import ref
         if ref.available():
             blobs = host_blobs(w)
-            threads = int(ref.lib().aclref_hardware_threads())
+            threads = ref.usable_threads()
             sample = bounded_sample(w, threads)
             seconds = cpu_reference_pass(w, blobs, sample, threads, 3)
             cpu_baseline = {"value": sample * w["num_tracks"] / seconds, "unit": unit, "cores": threads, "kind": "reference",
-                            "sample": f"{sample} of {num_requests} requests, fastest of 3 passes, acl::decompression_context<benchmark settings> on {threads} host threads"}
+                            "single_thread_value": sample_single_thread(w, blobs),
+                            "sample": f"{sample} of {num_requests} requests, fastest of 3 passes, acl::decompression_context<benchmark settings> (one context per clip, "
+                                      f"re-seek per request) on {threads} host threads (affinity / cgroup quota; hardware_concurrency = {os.cpu_count()})"}
         else:
             from oracle import port
             blobs = host_blobs(w)
@@ -537,19 +602,142 @@ def main() -> None:
             cpu_baseline = {"value": sample * w["num_tracks"] / seconds, "unit": unit, "cores": 1, "kind": "port",
                             "sample": f"{sample} of {num_requests} requests, plain-C port, 1 thread"}
 
+    # ---- the other BASELINE.json configs on this GPU (N = 1 only: value + roofline fraction + clocks per workload) ----
+    workloads = None
+    if world == 1 and not args.no_extra and args.workload == "c2" and args.clips is None:
+        del d_out
+        workloads = {}
+        for name in ("c3", "c5", "c4"):
+            workloads[name] = extra_workload(name, torch, ab, ctx, local_rank, peak, barrier)
+
     result = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": w["description"], "clips": "distinct" if w["distinct"] else "replicated", "clips_per_gpu": w["num_clips"],
-                   "requests_per_step_per_gpu": num_requests, "bones": w["num_tracks"], "layout": args.layout,
-                   "l2": f"inputs larger than L2: {clipset.blob_bytes / 1e6:.0f} MB compressed + {num_requests * pose_bytes / 1e6:.0f} MB of poses per step vs 126 MB L2",
-                   "math": MATH_DESCRIPTION[args.math if is_transform else "exact"], "parallelism": f"clip-sharded x{world}, no data-path collective"},
+        "config": workload_config(args, w, world, num_requests, pose_bytes, int(clipset.blob_bytes)),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "other_math": other_math, "gather": gather, "gpu_launches": int(gpu_launches), "clocks": clocks,
+        "per_rank_ms_per_step": per_rank_ms,
+        "upload": {"ms": upload_seconds * 1e3, "compressed_mb": clipset.blob_bytes / 1e6, "mb_per_s": clipset.blob_bytes / 1e6 / upload_seconds,
+                   "what": "aclb200_upload_clips_packed: validation + transcode into the HBM image (host threads) + H2D, once per clip set, never inside a timed region"},
+        "workloads": workloads, "c5_sharded": c5_sharded,
     }
     print(json.dumps(result))
     if distributed:
         dist.destroy_process_group()
+
+
+def sample_single_thread(w, blobs) -> float:
+    """The reference on ONE host thread (compare BASELINE.md: about 50 M bone-poses/s/core on the survey box)."""
+    sample = min(len(w["req_clip"]), max(1000, int(1.5 * 45e6 / max(w["num_tracks"], 1))))
+    seconds = cpu_reference_pass(w, blobs, sample, 1, 2)
+    return sample * w["num_tracks"] / seconds
+
+
+def extra_workload(name: str, torch, ab, ctx, local_rank: int, peak: float, barrier) -> dict:
+    """One of the other configs on the same GPU: a short timed run with its own clock record (steps sized so that the NVML poll
+    gets samples inside the region)."""
+    w = make_workload(name, 0, None)
+    is_transform = w["kind"] == "transform"
+    clipset = ctx.upload_packed(w["buffer"], w["offsets"], w["sizes"])
+    requests = ab.make_requests(w["req_clip"], w["req_time"])
+    n = len(requests)
+    options = ab.Options(output_layout=ab.LAYOUT_QVV40, math_mode=ab.MATH_EXACT)
+    bone_bytes = 40 if is_transform else 4 * clipset.components
+    d_requests = torch.from_numpy(requests.view(np.uint8)).cuda()
+    d_out = torch.empty(n * clipset.max_tracks * bone_bytes, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def launch():
+        if is_transform:
+            ctx.decompress_tracks(clipset, d_requests, n, options, d_out, stream)
+        else:
+            ctx.scalar_decompress_tracks(clipset, d_requests, n, options, d_out, stream)
+    alg = algorithmic_bytes_transform(w) if is_transform else algorithmic_bytes_scalar(w)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize()
+    probe0, probe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    probe0.record(stream); launch(); probe1.record(stream); torch.cuda.synchronize()
+    steps = int(min(400, max(20, 40.0 / max(probe0.elapsed_time(probe1), 1e-3))))       # about 40 ms of launches: tens of clock samples
+    elapsed_ms, kernel_ms = time_launches(torch, launch, stream, steps, 3, barrier, sampler)
+    clocks = sampler.stop()
+    achieved = alg["total"] / (kernel_ms * 1e-3) / 1e9
+    out = {"workload": w["description"], "value": alg["units"] * steps / (elapsed_ms * 1e-3), "unit": "bone-poses/s" if is_transform else "track-samples/s",
+           "steps": steps, "kernel_ms": kernel_ms, "math": "exact", "roofline": {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                                                                                "algorithmic_bytes_in": alg["in_bytes"], "algorithmic_bytes_out": alg["out_bytes"]},
+           "clocks": clocks}
+    clipset.release()
+    return out
+
+
+def routed_c5_job(args, torch, dist, ab, ctx, rank, local_rank, world, reducer, barrier, layout) -> dict:
+    """BASELINE.json configs[4]: ONE global list of world x 125 000 (clip, random t) requests over world x 125 000 small clips.
+    Every rank compresses a contiguous range of the clips; `partition_clips` then balances the ranges by compressed bytes and the
+    clips that change owner travel with one NCCL all_to_all over NVLink (the batch split); `route_requests` hands every rank the
+    requests of its clips (host side bucket: every rank holds the global list); decode; poses stay on the GPU that made them."""
+    from acl_b200 import sharding
+    w = make_workload("c5", rank, args.clips, world)
+    per_rank = w["num_clips"]
+    sizes_mine = w["sizes"].astype(np.int64)
+    all_sizes = [None] * world
+    dist.all_gather_object(all_sizes, sizes_mine)
+    sizes = np.concatenate(all_sizes)
+    generated = [(r * per_rank, (r + 1) * per_rank) for r in range(world)]
+    owner, local_index, bounds = sharding.partition_clips(sizes, world)
+    plan = sharding.exchange_plan(generated, bounds, sizes)
+    # this rank's clips back to back, without the generator's alignment padding
+    packed = np.concatenate([w["buffer"][int(o):int(o) + int(s)] for o, s in zip(w["offsets"], w["sizes"])])
+    t0 = time.perf_counter()
+    mine = sharding.redistribute_clips(torch.from_numpy(packed).cuda(), rank, plan)
+    torch.cuda.synchronize()
+    exchange_s = time.perf_counter() - t0
+    moved = sum(plan[rank][dst][2] for dst in range(world) if dst != rank)
+    lo, hi = bounds[rank]
+    my_sizes = sizes[lo:hi].astype(np.uint32)
+    # clips must sit at 16 byte aligned addresses for the upload's readers: re-pack with 64 byte strides
+    strides = (my_sizes.astype(np.int64) + 63) & ~63
+    my_offsets = np.concatenate([[0], np.cumsum(strides)[:-1]]).astype(np.uint64)
+    host_flat = mine.cpu().numpy()
+    raw = np.zeros(int(strides.sum()) + 128, dtype=np.uint8)
+    shift = (-raw.ctypes.data) % 64
+    buffer = raw[shift:shift + int(strides.sum()) + 64]
+    src = np.concatenate([[0], np.cumsum(my_sizes.astype(np.int64))])
+    for i in range(len(my_sizes)):
+        buffer[int(my_offsets[i]):int(my_offsets[i]) + int(my_sizes[i])] = host_flat[src[i]:src[i + 1]]
+    clipset = ctx.upload_packed(buffer, my_offsets, my_sizes)
+
+    # the global request list: every clip once, in random order, random time (same list on every rank)
+    rng = np.random.default_rng(11)
+    total_clips = world * per_rank
+    req_clip = rng.permutation(total_clips).astype(np.uint32)
+    req_time = (rng.random(total_clips) * (31 / 30.0)).astype(np.float32)
+    positions, local_clip, times = sharding.route_requests(req_clip, req_time, owner, local_index, rank)
+    requests = ab.make_requests(local_clip, times)
+    n = len(requests)
+    options = ab.Options(output_layout=layout, math_mode=ab.MATH_EXACT)
+    bone_bytes = 40 if layout == ab.LAYOUT_QVV40 else 48
+    d_requests = torch.from_numpy(requests.view(np.uint8)).cuda()
+    d_out = torch.empty(max(n, 1) * clipset.max_tracks * bone_bytes, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    steps = 200
+    rank_ms, kernel_ms = time_launches(torch, lambda: ctx.decompress_tracks(clipset, d_requests, n, options, d_out, stream), stream, steps, 5, barrier, sampler)
+    clocks = sampler.stop()
+    elapsed_ms = reducer.max(rank_ms)
+    units = n * 30
+    value = reducer.sum(units * steps) / (elapsed_ms * 1e-3)
+    per_rank = [None] * world
+    dist.all_gather_object(per_rank, {"requests": n, "clips": int(hi - lo), "ms_per_step": rank_ms / steps, "bytes_sent": int(moved)})
+    clipset.release()
+    return {"workload": f"C5 routed: {total_clips} clips x 30 bones x 32 samples over {world} GPUs, one global list of {total_clips} (clip, random t) requests",
+            "value": value, "unit": "bone-poses/s", "steps": steps, "ms_per_step": elapsed_ms / steps, "math": "exact",
+            "split": "partition_clips by compressed bytes; clips that change owner: one ncclAllToAll (all_to_all_single over NVLink); requests: host side bucket "
+                     "(route_requests on the global list every rank holds)",
+            "clip_exchange_ms": reducer.max(exchange_s * 1e3), "per_rank": per_rank, "clocks_rank0": clocks,
+            "data_path_collective": "none (poses stay sharded)"}
 
 
 if __name__ == "__main__":

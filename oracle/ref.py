@@ -266,11 +266,46 @@ def seek_info(blob: np.ndarray, t: float, rounding: int = ROUND_NONE, looping: i
 
 
 def bench(blobs: list[np.ndarray], request_clip: np.ndarray, request_time: np.ndarray, max_tracks: int,
-          num_threads: int, repeats: int = 1, scalar: bool = False) -> float:
-    """Seconds taken by the reference CPU path (fastest of `repeats` passes) for the request list."""
+          num_threads: int, repeats: int = 1, scalar: bool = False, out: np.ndarray | None = None) -> float:
+    """Seconds taken by the reference CPU path (fastest of `repeats` passes) for the request list. `out` (optional):
+    float32 [requests][max_tracks][12] (transform: rtm::qvvf as debug_track_writer stores it) / [requests][max_tracks][4] (scalar)."""
     ptrs = (C.c_void_p * len(blobs))(*[b.ctypes.data for b in blobs])
     request_clip = np.ascontiguousarray(request_clip, dtype=np.uint32)
     request_time = np.ascontiguousarray(request_time, dtype=np.float32)
     fn = lib().aclref_bench_scalar if scalar else lib().aclref_bench_transform
+    if out is not None:
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == request_clip.size * max_tracks * (4 if scalar else 12)
     return float(fn(C.cast(ptrs, C.c_void_p), request_clip.ctypes.data, request_time.ctypes.data, request_clip.size,
-                    max_tracks, num_threads, repeats, None))
+                    max_tracks, num_threads, repeats, None if out is None else out.ctypes.data))
+
+
+def decode_requests(blobs: list[np.ndarray], request_clip: np.ndarray, request_time: np.ndarray, max_tracks: int,
+                    num_threads: int = 0, scalar: bool = False) -> np.ndarray:
+    """Every request through the unmodified reference (acl::decompression_context<benchmark settings>, seek(t, none) +
+    decompress_tracks): float32 [requests][max_tracks][12] (scalar clips: [requests][max_tracks][4], one float per float1f track)."""
+    out = np.zeros((len(request_clip), max_tracks, 4 if scalar else 12), dtype=np.float32)
+    bench(blobs, request_clip, request_time, max_tracks, num_threads or usable_threads(), 1, scalar=scalar, out=out)
+    return out
+
+
+def usable_threads() -> int:
+    """Host threads this process may really use: the scheduler affinity, bounded by the cgroup CPU quota (a container lease often
+    exposes every core of the box through hardware_concurrency() while the quota grants a fraction of them)."""
+    import math
+    import os
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            text = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if text[0] != "max":
+                    threads = min(threads, max(1, math.ceil(int(text[0]) / int(text[1]))))
+            else:
+                quota = int(text[0])
+                period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if quota > 0:
+                    threads = min(threads, max(1, math.ceil(quota / period)))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return max(1, threads)

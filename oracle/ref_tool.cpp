@@ -703,10 +703,12 @@ extern "C"
 		return 0;
 	}
 
-	// CPU baseline: the reference's own decompression_context<benchmark settings>, one context per request
-	// batch entry, requests split statically over `num_threads` threads. `out` may be null (then every
-	// thread writes into a private scratch pose, like the reference benchmark does) or point at
-	// [num_requests][max_tracks][12] floats. Returns elapsed seconds of the fastest of `repeats` passes.
+	// CPU baseline: the reference's own decompression_context<benchmark settings>, requests split statically over
+	// `num_threads` threads. Like the reference benchmark (tools/acl_decompressor/sources/benchmark.cpp:246-258) a context
+	// stays bound to its clip: a thread re-initialises its context only when the request's clip changes, then seek +
+	// decompress_tracks per request. `out` may be null (then every thread writes into a private scratch pose, like the
+	// reference benchmark does) or point at [num_requests][max_tracks][12] floats (the parity tests). Returns elapsed seconds
+	// of the fastest of `repeats` passes.
 	double aclref_bench_transform(const void* const* blobs, const uint32_t* request_clip, const float* request_time,
 		uint32_t num_requests, uint32_t max_tracks, uint32_t num_threads, uint32_t repeats, float* out)
 	{
@@ -737,7 +739,8 @@ extern "C"
 					for (uint64_t request = begin; request < end; ++request)
 					{
 						const compressed_tracks* tracks = static_cast<const compressed_tracks*>(blobs[request_clip[request]]);
-						context.initialize(*tracks);
+						if (context.get_compressed_tracks() != tracks)
+							context.initialize(*tracks);
 						context.seek(request_time[request], sample_rounding_policy::none);
 						writer.out = out != nullptr ? out + request * size_t(max_tracks) * 12 : scratch.data();
 						context.decompress_tracks(writer);
@@ -786,7 +789,8 @@ extern "C"
 					for (uint64_t request = begin; request < end; ++request)
 					{
 						const compressed_tracks* tracks = static_cast<const compressed_tracks*>(blobs[request_clip[request]]);
-						context.initialize(*tracks);
+						if (context.get_compressed_tracks() != tracks)
+							context.initialize(*tracks);
 						context.seek(request_time[request], sample_rounding_policy::none);
 						writer.out = out != nullptr ? out + request * size_t(max_tracks) * 4 : scratch.data();
 						context.decompress_tracks(writer);

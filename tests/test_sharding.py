@@ -25,9 +25,12 @@ def test_partition_is_contiguous_and_balanced():
         assert all(owner[lo:hi] == r)
     shard_bytes = [sum(sizes[lo:hi]) for lo, hi in bounds]
     assert max(shard_bytes) <= 0.75 * sum(sizes)
-    # more ranks than clips: the extra ranks get empty shards, nothing is lost
-    owner, local, bounds = sharding.partition_clips([10, 10], 4)
-    assert sum(hi - lo for lo, hi in bounds) == 2
+    # more ranks than clips: a rank without clips could not build a clip set and would hang the job's collectives -> refused up front
+    with pytest.raises(ValueError):
+        sharding.partition_clips([10, 10], 4)
+    # one clip that dominates the byte total: several ideal cuts collapse onto it, every rank still gets a clip
+    owner, local, bounds = sharding.partition_clips([10, 10, 100000, 10, 10], 4)
+    assert all(hi > lo for lo, hi in bounds) and bounds[-1][1] == 5
 
 
 def test_route_requests_covers_every_request_once():
@@ -106,24 +109,64 @@ def test_two_rank_sharded_decode_matches_single_process(tmp_path):
     assert job == pytest.approx(64 / 2.0)      # all units over the slowest rank's time
 
 
+def _exchange_worker(rank, world, port, result_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # every rank "generates" a contiguous range of clips (like bench.py's ranks compress their own clips), the byte balanced
+        # partition moves the boundary: the clips in between travel with one all_to_all
+        sizes = [300, 100, 100, 100, 100, 100, 100, 100]
+        payload = [np.full(size, clip + 1, dtype=np.uint8) for clip, size in enumerate(sizes)]
+        generated = [(0, 4), (4, 8)]
+        owner, local, bounds = sharding.partition_clips(sizes, world)
+        plan = sharding.exchange_plan(generated, bounds, sizes)
+        lo, hi = generated[rank]
+        mine = torch.from_numpy(np.concatenate(payload[lo:hi]))
+        received = sharding.redistribute_clips(mine, rank, plan).numpy()
+        o_lo, o_hi = bounds[rank]
+        expected = np.concatenate(payload[o_lo:o_hi])
+        ok = np.array_equal(received, expected)
+        results = [None] * world
+        dist.all_gather_object(results, (ok, bounds))
+        if rank == 0:
+            np.save(result_path, np.array([float(all(r[0] for r in results)), float(bounds[0][1])]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_clip_exchange_follows_the_byte_balanced_partition(tmp_path):
+    world = 2
+    result_path = str(tmp_path / "exchange.npy")
+    mp.spawn(_exchange_worker, args=(world, _free_port(), result_path), nprocs=world, join=True)
+    ok, first_cut = np.load(result_path)
+    assert ok == 1.0
+    assert first_cut != 4       # the partition did move the boundary, so clips really travelled
+
+
 def test_partition_and_routing_properties():
     """Property test: any sizes / world / request list -> contiguous cover, every request routed exactly once to the owner of its clip."""
     from hypothesis import given, settings, strategies as st
 
     @settings(max_examples=200, deadline=None)
-    @given(sizes=st.lists(st.integers(min_value=1, max_value=10_000), min_size=0, max_size=40),
+    @given(sizes=st.lists(st.integers(min_value=1, max_value=10_000), min_size=1, max_size=40),
            world=st.integers(min_value=1, max_value=9),
            picks=st.lists(st.integers(min_value=0, max_value=60), min_size=0, max_size=80))
     def check(sizes, world, picks):
+        if len(sizes) < world:
+            with pytest.raises(ValueError):
+                sharding.partition_clips(sizes, world)
+            return
         owner, local, bounds = sharding.partition_clips(sizes, world)
         assert len(bounds) == world and bounds[0][0] == 0 and bounds[-1][1] == len(sizes)
         for r in range(world - 1):
             assert bounds[r][1] == bounds[r + 1][0]
         for r, (lo, hi) in enumerate(bounds):
+            assert hi > lo, "no rank may end up without clips"
             assert all(owner[lo:hi] == r) and list(local[lo:hi]) == list(range(hi - lo))
-        if sizes:
-            # no shard is heavier than its fair share plus one clip
-            fair = sum(sizes) / world
+        # no shard is heavier than its fair share plus one clip, unless keeping every shard non-empty forced a cut
+        fair = sum(sizes) / world
+        if all(hi - lo > 1 for lo, hi in bounds):
             assert max(sum(sizes[lo:hi]) for lo, hi in bounds) <= fair + max(sizes)
         req_clip = np.array(picks, dtype=np.uint32)
         req_time = np.arange(len(picks), dtype=np.float32)
