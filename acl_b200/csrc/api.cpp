@@ -301,6 +301,7 @@ extern "C"
 		if (status != ACLB200_OK || num_requests == 0)
 			return status;
 		cudaSetDevice(context->device);
+		plan_scalar_launch(params, clipset->max_key_frame_bytes);
 		return finish_launch(context, launch_scalar_decompress_tracks(params, static_cast<cudaStream_t>(stream)), "scalar_decompress_tracks");
 	}
 

@@ -208,11 +208,39 @@ namespace aclb200
 				std::memcpy(image.at(d.const_rot_offset), blob + constant_offset, size_t(constant_index) * 4);
 				d.const_vec_offset = image.reserve(size_t(range_index) * 4 + 16);
 				std::memcpy(image.at(d.const_vec_offset), blob + range_offset, size_t(range_index) * 4);
+				// the same values once more, indexed by track: min[components], extent[components]
+				d.track_range_offset = image.reserve(size_t(num_tracks) * num_components * 8 + 16);
+				for (uint32_t track = 0; track < num_tracks; ++track)
+				{
+					ScalarTrackDesc desc;
+					std::memcpy(&desc, image.at(d.bone_table_offset) + size_t(track) * sizeof(ScalarTrackDesc), sizeof(desc));
+					const uint32_t num_bits = desc.value_index_and_bits & 0xFFu, value_index = desc.value_index_and_bits >> 8;
+					float* row = reinterpret_cast<float*>(image.at(d.track_range_offset)) + size_t(track) * num_components * 2;
+					for (uint32_t c = 0; c < num_components; ++c)
+					{
+						if (num_bits == 0)
+						{
+							row[c] = rd_f32(blob + constant_offset + (value_index + c) * 4);
+							row[num_components + c] = 0.0F;
+						}
+						else if (num_bits == 32)
+						{
+							row[c] = 0.0F;
+							row[num_components + c] = 1.0F;
+						}
+						else
+						{
+							row[c] = rd_f32(blob + range_offset + (value_index + c) * 4);
+							row[num_components + c] = rd_f32(blob + range_offset + (value_index + num_components + c) * 4);
+						}
+					}
+				}
 				d.seg_table_offset = append_stream(image, blob + animated_offset, size_t(stream_bytes));
 
 				d.num_segments = 1;
 				d.samples_per_segment = num_samples;
 				d.num_animated_total = num_bits_per_frame;
+				out.max_key_frame_bytes = (num_bits_per_frame + 7) / 8;
 				d.image_size = image.reserve(0);
 				return std::string();
 			}
@@ -742,8 +770,7 @@ namespace aclb200
 					set->max_animated_total = desc.num_animated_total > set->max_animated_total ? desc.num_animated_total : set->max_animated_total;
 				}
 			}
-			if (set_track_type == k_track_qvvf)
-				for (const range_result& result : results)
+			for (const range_result& result : results)
 					set->max_key_frame_bytes = result.max_key_frame_bytes > set->max_key_frame_bytes ? result.max_key_frame_bytes : set->max_key_frame_bytes;
 			total_image_bytes += k_stream_tail;
 

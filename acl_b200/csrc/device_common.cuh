@@ -24,6 +24,18 @@ namespace aclb200
 		__device__ __forceinline__ float fnegmulsub(float a, float b, float c) { return __fsub_rn(c, __fmul_rn(a, b)); }
 		__device__ __forceinline__ float u2f(uint32_t v) { return __uint2float_rn(v); }
 
+		// ---- packed f32x2 arithmetic ----
+		// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into a single-rounding FFMA2 even under --fmad=false, which would break the
+		// bit-exact contract. The add is therefore issued as fma(product, one, addend) with `one` a RUN-TIME 1.0f (DecodeParams::one):
+		// round(product * 1 + addend) == round(product + addend), and ptxas cannot fold a multiplier it does not know.
+		__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+		__device__ __forceinline__ float2 mul2(float2 a, float b) { return __fmul2_rn(a, make_float2(b, b)); }
+		__device__ __forceinline__ float2 add2(float2 a, float2 b, float one) { return __ffma2_rn(a, make_float2(one, one), b); }		// a + b
+		__device__ __forceinline__ float2 sub2(float2 a, float2 b, float one) { return __ffma2_rn(b, make_float2(-one, -one), a); }	// a - b
+		__device__ __forceinline__ float2 muladd2(float2 a, float2 b, float2 c, float one) { return __ffma2_rn(__fmul2_rn(a, b), make_float2(one, one), c); }
+		__device__ __forceinline__ float2 muladd2(float2 a, float b, float c, float one) { return __ffma2_rn(__fmul2_rn(a, make_float2(b, b)), make_float2(one, one), make_float2(c, c)); }
+		__device__ __forceinline__ float2 negmulsub2(float2 a, float2 b, float2 c, float one) { return __ffma2_rn(__fmul2_rn(a, b), make_float2(-one, -one), c); }
+
 		// ---------------------------------------------------------------------------------------------------
 		// TMA bulk copy + mbarrier (PTX ISA: cp.async.bulk, mbarrier)
 		// ---------------------------------------------------------------------------------------------------

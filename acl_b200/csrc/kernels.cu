@@ -26,6 +26,8 @@
 // are bit-identical to the reference's SSE2/AVX/scalar builds for decompress_tracks.
 #include "device_common.cuh"
 
+#include <type_traits>
+
 namespace aclb200
 {
 	using namespace dev;
@@ -373,37 +375,292 @@ namespace aclb200
 			}
 		}
 
-		template<int COMPONENTS, bool PER_TRACK>
-		__global__ void __launch_bounds__(k_threads_per_block)
-		scalar_decompress_tracks_kernel(const DecodeParams p)
+		// ---------------------------------------------------------------------------------------------------
+		// scalar decompress_tracks, chained: a block takes a batch of consecutive requests. Warp 0 runs the seek (one lane per request)
+		// and groups the requests that play one clip forward (request i + 1 starts on the key frame request i ends on): a group's key
+		// frames are ONE contiguous piece of the clip's bit stream, staged in shared memory by one TMA copy. Then one thread per
+		// (group, track): the track's descriptor and range are loaded once per group, every key frame value is unpacked once
+		// (n + 1 unpacks for n requests instead of 2 n), and each request's sample leaves with a coalesced store (consecutive threads
+		// hold consecutive tracks). Groups whose window does not fit the pool read the stream from global memory instead.
+		// ---------------------------------------------------------------------------------------------------
+		constexpr uint32_t k_scalar_threads = 256;
+		constexpr uint32_t k_scalar_max_batch = 32;
+
+		struct alignas(16) ScalarHot
 		{
-			__shared__ ScalarReqState s_req[k_max_requests_per_block];
+			const uint8_t* image;
+			uint8_t* out;
+			float    alpha;					// (alpha, bit1) are read together, once per request and thread
+			uint32_t bit1;					// key frame bit addresses: inside the pool (staged) or inside the clip's stream
+			uint32_t bit0;
+			uint32_t num_tracks;			// 0 => invalid request
+			uint32_t tracks_off, constant_off, range_off, stream_off;
+			uint32_t group;					// (first request) | (count << 8) | (staged << 16), valid on the group's first request
+			uint32_t track_range_off;
+		};
+		static_assert(sizeof(ScalarHot) == 64, "ScalarHot is 64 bytes");
+
+		template<int COMPONENTS>
+		__device__ __forceinline__ void scalar_key_frame_value(const uint32_t* pool_words, const uint32_t* stream_words, bool staged, uint32_t bit, uint32_t num_bits,
+			float inv_max, const float range_min[COMPONENTS], const float range_extent[COMPONENTS], float value[COMPONENTS])
+		{
+			const uint32_t* words = staged ? pool_words : stream_words;
+#pragma unroll
+			for (int c = 0; c < COMPONENTS; ++c)
+			{
+				const uint32_t at = bit + (num_bits == 32 ? 32u : num_bits) * c;
+				const uint32_t hi = staged ? words[at >> 5] : __ldg(words + (at >> 5));
+				const uint32_t lo = staged ? words[(at >> 5) + 1] : __ldg(words + (at >> 5) + 1);
+				const uint32_t raw = __funnelshift_l(lo, hi, at & 31);
+				if (num_bits == 32)
+					value[c] = __uint_as_float(raw);
+				else
+					value[c] = fmuladd(fmul(u2f(raw >> (32 - num_bits)), inv_max), range_extent[c], range_min[c]);		// decompression.scalar.h:317-346
+			}
+		}
+
+		template<int COMPONENTS, bool PER_TRACK>
+		__global__ void __launch_bounds__(k_scalar_threads)
+		scalar_tracks_pipeline_kernel(const DecodeParams p)
+		{
+			extern __shared__ __align__(16) uint8_t s_dynamic[];		// the key frame pool
+			__shared__ ScalarHot s_hot[k_scalar_max_batch];
+			__shared__ __align__(8) uint64_t s_barrier;
+			__shared__ uint32_t s_num_groups;
+			__shared__ uint32_t s_group_first[k_scalar_max_batch];
 
 			const uint32_t first_request = blockIdx.x * p.requests_per_block;
 			const uint32_t num_requests = min(p.requests_per_block, p.num_requests - first_request);
-			if (threadIdx.x < num_requests)
-			{
-				ScalarReqState rs;
-				seek_scalar(p, first_request + threadIdx.x, rs);
-				rs.out = p.out + uint64_t(first_request + threadIdx.x) * p.pose_stride;
-				s_req[threadIdx.x] = rs;
-			}
+			const uint32_t pool_bytes = p.smem_bytes;
+			if (threadIdx.x == 0)
+				mbar_init(&s_barrier, 32);
 			__syncthreads();
 
-			const uint32_t num_slots = num_requests * p.max_tracks;
-			for (uint32_t slot = threadIdx.x; slot < num_slots; slot += k_threads_per_block)
+			if (threadIdx.x < 32)
 			{
-				const uint32_t local_request = fast_div(slot, p.magic_tracks);
-				const uint32_t track = slot - local_request * p.max_tracks;
-				const ScalarReqState& rs = s_req[local_request];
-				if (track >= rs.num_tracks)
-					continue;
-				float value[COMPONENTS];
-				decode_scalar_track<COMPONENTS, PER_TRACK>(p, rs, track, value);
-				float* dst = reinterpret_cast<float*>(rs.out) + size_t(track) * COMPONENTS;
+				// ---- seek + grouping + window staging, one lane per request ----
+				const uint32_t lane = threadIdx.x;
+				const bool active = lane < num_requests;
+				ScalarReqState rs;
+				rs.num_tracks = 0;
+				uint32_t clip_index = 0xFFFFFFFFu, bits_per_frame = 0;
+				if (active)
+				{
+					seek_scalar(p, first_request + lane, rs);
+					if (rs.num_tracks != 0)
+					{
+						clip_index = p.requests[first_request + lane].clip;
+						bits_per_frame = p.clips[clip_index].num_animated_total;
+					}
+				}
+				const bool valid = rs.num_tracks != 0;
+				const uint32_t kf0 = valid ? rs.kf_bit[0] : 0u, kf1 = valid ? rs.kf_bit[1] : 0u;
+				const bool mergeable = valid && kf1 >= kf0 && bits_per_frame != 0;
+				const uint32_t prev_clip = __shfl_up_sync(0xFFFFFFFFu, mergeable ? clip_index : 0xFFFFFFFFu, 1);
+				const uint32_t prev_kf1 = __shfl_up_sync(0xFFFFFFFFu, kf1, 1);
+				const bool join = lane > 0 && mergeable && clip_index == prev_clip && kf0 == prev_kf1;
+				const uint32_t lanes_le = 0xFFFFFFFFu >> (31 - lane);
+				const uint32_t heads = __ballot_sync(0xFFFFFFFFu, !join);
+				const uint32_t group_start = 31 - __clz(heads & lanes_le);
+				const uint32_t heads_after = lane == 31 ? 0u : (heads & (0xFFFFFFFEu << lane));
+				const uint32_t group_end = heads_after != 0 ? uint32_t(__ffs(heads_after) - 1) : 32u;
+				const bool head = !join;
+				const uint32_t head_kf0 = __shfl_sync(0xFFFFFFFFu, kf0, group_start);
+				const uint32_t last_kf1 = __shfl_sync(0xFFFFFFFFu, kf1, (group_end - 1) & 31);
+
+				// the group's window: 16 byte aligned start, every key frame from the first request's first to the last request's second,
+				// 16 bytes of tail for the last value's second word
+				const uint32_t src_byte = (head_kf0 >> 3) & ~15u;
+				uint32_t window_bytes = 0;
+				if (head && mergeable)
+					window_bytes = ((((last_kf1 + bits_per_frame - src_byte * 8) + 7) >> 3) + 16 + 15) & ~15u;
+				// pool offsets: exclusive prefix sum of the heads' window sizes
+				uint32_t offset = window_bytes;
 #pragma unroll
-				for (int c = 0; c < COMPONENTS; ++c)
-					dst[c] = value[c];
+				for (uint32_t d = 1; d < 32; d <<= 1)
+				{
+					const uint32_t below = __shfl_up_sync(0xFFFFFFFFu, offset, d);
+					if (lane >= d)
+						offset += below;
+				}
+				offset -= window_bytes;
+				const bool staged_head = head && mergeable && window_bytes != 0 && offset + window_bytes <= pool_bytes;
+				const bool staged = __shfl_sync(0xFFFFFFFFu, staged_head, group_start);
+				const uint32_t window_offset = __shfl_sync(0xFFFFFFFFu, offset, group_start);
+
+				if (active)
+				{
+					ScalarHot h;
+					h.image = rs.image;
+					h.out = p.out + uint64_t(first_request + lane) * p.pose_stride;
+					h.alpha = rs.alpha;
+					h.num_tracks = rs.num_tracks;
+					h.tracks_off = valid ? uint32_t(reinterpret_cast<const uint8_t*>(rs.tracks) - rs.image) : 0u;
+					h.constant_off = rs.constant_off;
+					h.range_off = rs.range_off;
+					h.stream_off = rs.stream_off;
+					h.bit0 = staged ? window_offset * 8 + (kf0 - src_byte * 8) : kf0;
+					h.bit1 = staged ? window_offset * 8 + (kf1 - src_byte * 8) : kf1;
+					h.group = lane | ((group_end - group_start) << 8) | (staged ? 1u << 16 : 0u);
+					h.track_range_off = clip_index != 0xFFFFFFFFu ? p.clips[clip_index].track_range_offset : 0u;
+					s_hot[lane] = h;
+				}
+				if (head && active)
+					s_group_first[__popc(heads & lanes_le) - 1] = lane;
+				if (lane == 0)
+					s_num_groups = __popc(heads & (num_requests >= 32 ? 0xFFFFFFFFu : ((1u << num_requests) - 1u)));
+				if (staged_head && active)
+				{
+					mbar_arrive_expect_tx(&s_barrier, window_bytes);
+					bulk_copy_g2s(s_dynamic + offset, rs.image + rs.stream_off + src_byte, window_bytes, &s_barrier);
+				}
+				else
+					mbar_arrive(&s_barrier);
+			}
+			__syncthreads();
+			mbar_wait(&s_barrier, 0);
+
+			// ---- group by group, one thread per track ----
+			// The chain: request r interpolates (value at its first key frame, value at its second); its second key frame is the next
+			// request's first, so each request costs ONE unpack. Requests go two at a time: the two new key frame values travel as one
+			// f32x2 pair through the range expansion and the interpolation (exact: see muladd2 in device_common.cuh). Constant tracks
+			// ride along (their range is (constant, 0)) and a final select keeps the constant itself, as the reference writes it
+			// (decompression.scalar.h:289-315): no divergence between the lanes of a warp.
+			const uint32_t* pool_words = reinterpret_cast<const uint32_t*>(s_dynamic);
+			const float one = p.one;
+			const uint64_t pose_stride = p.pose_stride;
+			const uint32_t num_groups = s_num_groups;
+			for (uint32_t group = 0; group < num_groups; ++group)
+			{
+				const uint32_t first = s_group_first[group];
+				const ScalarHot& h0 = s_hot[first];
+				const uint32_t num_tracks = h0.num_tracks;
+				if (num_tracks == 0)
+					continue;
+				const uint32_t count = (h0.group >> 8) & 0xFFu;
+				const bool staged = (h0.group >> 16) != 0;
+				const uint4* descs = reinterpret_cast<const uint4*>(h0.image + h0.tracks_off);		// ScalarTrackDesc
+				const float* ranges = reinterpret_cast<const float*>(h0.image + h0.track_range_off);
+				const uint32_t* stream_words = reinterpret_cast<const uint32_t*>(h0.image + h0.stream_off);
+				const uint32_t first_bit = h0.bit0;
+				uint8_t* group_out = h0.out;
+				const uint32_t hot_addr = smem_u32(&s_hot[first].alpha);
+
+				auto tracks_loop = [&](auto staged_tag)
+				{
+					constexpr bool STAGED = decltype(staged_tag)::value;
+					const uint32_t* words = STAGED ? pool_words : stream_words;
+					auto word = [&](uint32_t index) { return STAGED ? words[index] : __ldg(words + index); };
+					auto store = [&](uint8_t* row, int c, float v) { asm volatile("st.global.f32 [%0], %1;" :: "l"(row + c * 4), "f"(v) : "memory"); };
+					auto load_track = [&](uint32_t track, uint4& desc, float range_min[COMPONENTS], float range_extent[COMPONENTS])
+					{
+						desc = make_uint4(0, 1, 0, 0);
+						if (track >= num_tracks)
+							return;
+						desc = __ldg(descs + track);
+#pragma unroll
+						for (int c = 0; c < COMPONENTS; ++c)
+						{
+							range_min[c] = __ldg(ranges + size_t(track) * COMPONENTS * 2 + c);
+							range_extent[c] = __ldg(ranges + size_t(track) * COMPONENTS * 2 + COMPONENTS + c);
+						}
+					};
+					// the next track's descriptor and range are requested while the current track is being decoded
+					uint4 next_desc;
+					float next_min[COMPONENTS], next_extent[COMPONENTS];
+					load_track(threadIdx.x, next_desc, next_min, next_extent);
+					for (uint32_t track = threadIdx.x; track < num_tracks; track += k_scalar_threads)
+					{
+						const uint4 desc = next_desc;
+						float range_min[COMPONENTS], range_extent[COMPONENTS];
+#pragma unroll
+						for (int c = 0; c < COMPONENTS; ++c)
+						{
+							range_min[c] = next_min[c];
+							range_extent[c] = next_extent[c];
+						}
+						load_track(track + k_scalar_threads, next_desc, next_min, next_extent);
+
+						const uint32_t stored_bits = desc.y & 0xFFu;
+						const bool constant = stored_bits == 0;
+						const float inv_max = __uint_as_float(desc.z);
+						const uint32_t policy = PER_TRACK ? track_rounding_policy(p, track) : ACLB200_ROUND_NONE;
+						uint8_t* out = group_out + size_t(track) * COMPONENTS * 4;
+						if (stored_bits == 32)
+						{
+							// raw 32 bit samples: no range, plain interpolation (rare: the compressor keeps them for tracks it cannot quantise)
+							float start[COMPONENTS];
+							scalar_key_frame_value<COMPONENTS>(pool_words, stream_words, STAGED, first_bit + desc.x, 32, inv_max, range_min, range_extent, start);
+							for (uint32_t r = 0; r < count; ++r)
+							{
+								uint2 h;
+								asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(h.x), "=r"(h.y) : "r"(hot_addr + r * uint32_t(sizeof(ScalarHot))));
+								float end[COMPONENTS];
+								scalar_key_frame_value<COMPONENTS>(pool_words, stream_words, STAGED, h.y + desc.x, 32, inv_max, range_min, range_extent, end);
+								const float alpha = PER_TRACK ? apply_rounding_policy(__uint_as_float(h.x), policy) : __uint_as_float(h.x);
+#pragma unroll
+								for (int c = 0; c < COMPONENTS; ++c)
+								{
+									store(out + uint64_t(r) * pose_stride, c, lerp(start[c], end[c], alpha));
+									start[c] = end[c];
+								}
+							}
+							continue;
+						}
+
+						const uint32_t num_bits = constant ? 1u : stored_bits;		// constant tracks: any defined shift, the value is replaced below
+						const uint32_t down = 32 - num_bits;
+						auto unpack = [&](uint32_t at) { return __funnelshift_l(word((at >> 5) + 1), word(at >> 5), at & 31) >> down; };
+						float start[COMPONENTS];
+#pragma unroll
+						for (int c = 0; c < COMPONENTS; ++c)
+							start[c] = fmuladd(fmul(u2f(unpack(first_bit + desc.x + num_bits * c)), inv_max), range_extent[c], range_min[c]);		// decompression.scalar.h:317-346
+						uint32_t r = 0;
+						for (; r + 2 <= count; r += 2)
+						{
+							uint2 ha, hb;		// (alpha, bit1) of requests r and r + 1
+							asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ha.x), "=r"(ha.y) : "r"(hot_addr + r * uint32_t(sizeof(ScalarHot))));
+							asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(hb.x), "=r"(hb.y) : "r"(hot_addr + (r + 1) * uint32_t(sizeof(ScalarHot))));
+							float alpha_a = __uint_as_float(ha.x), alpha_b = __uint_as_float(hb.x);
+							if (PER_TRACK)
+							{
+								alpha_a = apply_rounding_policy(alpha_a, policy);		// decompression.scalar.h:235-247,273-280
+								alpha_b = apply_rounding_policy(alpha_b, policy);
+							}
+							const float2 alpha = make_float2(alpha_a, alpha_b);
+							uint8_t* row_a = out + uint64_t(r) * pose_stride;
+							uint8_t* row_b = row_a + pose_stride;
+#pragma unroll
+							for (int c = 0; c < COMPONENTS; ++c)
+							{
+								float2 end = mul2(make_float2(u2f(unpack(ha.y + desc.x + num_bits * c)), u2f(unpack(hb.y + desc.x + num_bits * c))), inv_max);
+								end = muladd2(end, range_extent[c], range_min[c], one);
+								const float2 begin = make_float2(start[c], end.x);
+								// rtm::scalar_lerp / vector_lerp: end * alpha + (start - start * alpha)
+								const float2 value = add2(mul2(end, alpha), sub2(begin, mul2(begin, alpha), one), one);
+								store(row_a, c, constant ? range_min[c] : value.x);
+								store(row_b, c, constant ? range_min[c] : value.y);
+								start[c] = end.y;
+							}
+						}
+						if (r < count)
+						{
+							uint2 h;
+							asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(h.x), "=r"(h.y) : "r"(hot_addr + r * uint32_t(sizeof(ScalarHot))));
+							const float alpha = PER_TRACK ? apply_rounding_policy(__uint_as_float(h.x), policy) : __uint_as_float(h.x);
+#pragma unroll
+							for (int c = 0; c < COMPONENTS; ++c)
+							{
+								const float end = fmuladd(fmul(u2f(unpack(h.y + desc.x + num_bits * c)), inv_max), range_extent[c], range_min[c]);
+								store(out + uint64_t(r) * pose_stride, c, constant ? range_min[c] : lerp(start[c], end, alpha));
+							}
+						}
+					}
+				};
+				if (staged)
+					tracks_loop(std::true_type());
+				else
+					tracks_loop(std::false_type());
 			}
 		}
 
@@ -573,18 +830,53 @@ namespace aclb200
 		return cudaGetLastError();
 	}
 
+	// The key frame pool of the chained scalar kernel: 4 blocks of 48 KB + statics stay resident per SM
+#ifndef ACLB200_SCALAR_POOL_KB
+#define ACLB200_SCALAR_POOL_KB 48
+#endif
+	constexpr uint32_t k_scalar_pool_bytes = ACLB200_SCALAR_POOL_KB * 1024u;
+
+	template<int COMPONENTS, bool PER_TRACK>
+	static cudaError_t launch_scalar_pipeline(const DecodeParams& params, cudaStream_t stream)
+	{
+		static bool configured = false;		// (idempotent; a race only repeats the call)
+		if (!configured)
+		{
+			const cudaError_t error = cudaFuncSetAttribute(scalar_tracks_pipeline_kernel<COMPONENTS, PER_TRACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(k_scalar_pool_bytes));
+			if (error != cudaSuccess)
+				return error;
+			configured = true;
+		}
+		const uint32_t blocks = (params.num_requests + params.requests_per_block - 1) / params.requests_per_block;
+		scalar_tracks_pipeline_kernel<COMPONENTS, PER_TRACK><<<blocks, k_scalar_threads, params.smem_bytes, stream>>>(params);
+		return cudaGetLastError();
+	}
+
 	template<bool PER_TRACK>
 	static cudaError_t launch_scalar_tracks(const DecodeParams& params, uint32_t components, cudaStream_t stream)
 	{
-		const uint32_t blocks = (params.num_requests + params.requests_per_block - 1) / params.requests_per_block;
 		switch (components)
 		{
-		case 1: scalar_decompress_tracks_kernel<1, PER_TRACK><<<blocks, k_threads_per_block, 0, stream>>>(params); break;
-		case 2: scalar_decompress_tracks_kernel<2, PER_TRACK><<<blocks, k_threads_per_block, 0, stream>>>(params); break;
-		case 3: scalar_decompress_tracks_kernel<3, PER_TRACK><<<blocks, k_threads_per_block, 0, stream>>>(params); break;
-		default: scalar_decompress_tracks_kernel<4, PER_TRACK><<<blocks, k_threads_per_block, 0, stream>>>(params); break;
+		case 1: return launch_scalar_pipeline<1, PER_TRACK>(params, stream);
+		case 2: return launch_scalar_pipeline<2, PER_TRACK>(params, stream);
+		case 3: return launch_scalar_pipeline<3, PER_TRACK>(params, stream);
+		default: return launch_scalar_pipeline<4, PER_TRACK>(params, stream);
 		}
-		return cudaGetLastError();
+	}
+
+	// requests per block and the key frame pool of a scalar decompress_tracks launch: as many requests as chained key frames fit the pool
+	void plan_scalar_launch(DecodeParams& params, uint32_t max_key_frame_bytes)
+	{
+		const uint32_t frame_bytes = max_key_frame_bytes + 48;
+		uint32_t requests_per_block = frame_bytes != 0 ? k_scalar_pool_bytes / frame_bytes : 1;
+		if (requests_per_block > 1) --requests_per_block;		// n chained requests read n + 1 key frames
+		if (requests_per_block < 1) requests_per_block = 1;
+		if (requests_per_block > k_scalar_max_batch) requests_per_block = k_scalar_max_batch;
+		// small clips: keep a block busy with at least ~4096 (request, track) items when the pool allows
+		params.requests_per_block = requests_per_block;
+		params.smem_bytes = k_scalar_pool_bytes;
+		params.one = 1.0f;
+		params.magic_tracks = division_magic(params.max_tracks == 0 ? 1 : params.max_tracks);
 	}
 
 	template<bool PER_TRACK>

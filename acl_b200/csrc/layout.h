@@ -80,7 +80,9 @@ namespace aclb200
 		uint32_t image_size;
 		uint32_t hash;						// compressed_tracks::get_hash()
 		uint32_t size;						// compressed_tracks::get_size()
-		uint32_t pad[2];
+		uint32_t track_range_offset;		// scalar clips: float[num_tracks][2 * components] = range min, range extent of every track (constant
+											// tracks: the constant, 0; raw tracks: 0, 1), so that a thread finds them without the descriptor's index
+		uint32_t pad;
 	};
 	static_assert(sizeof(ClipDesc) % 16 == 0, "ClipDesc must stay 16 byte sized");
 
