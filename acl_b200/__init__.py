@@ -12,4 +12,5 @@ from .api import (  # noqa: F401
     NORMALIZE_NEVER, NORMALIZE_LERP_ONLY, NORMALIZE_ALWAYS,
     DEFAULT_SKIPPED, DEFAULT_CONSTANT, DEFAULT_VARIABLE, DEFAULT_LEGACY,
     LAYOUT_QVV48, LAYOUT_QVV40, MATH_EXACT, MATH_FAST, TRACK_QVVF,
+    SKIP_ROTATION, SKIP_TRANSLATION, SKIP_SCALE,
 )

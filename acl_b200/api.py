@@ -15,6 +15,7 @@ NORMALIZE_NEVER, NORMALIZE_LERP_ONLY, NORMALIZE_ALWAYS = 0, 1, 2
 DEFAULT_SKIPPED, DEFAULT_CONSTANT, DEFAULT_VARIABLE, DEFAULT_LEGACY = 0, 1, 2, 3
 LAYOUT_QVV48, LAYOUT_QVV40 = 0, 1
 MATH_EXACT, MATH_FAST = 0, 1
+SKIP_ROTATION, SKIP_TRANSLATION, SKIP_SCALE = 1, 2, 4
 TRACK_QVVF = 12
 
 # numpy view of aclb200_request {uint32 clip; float sample_time}
@@ -45,6 +46,7 @@ class Options(C.Structure):
         ("d_variable_defaults", C.c_void_p), ("d_per_track_rounding", C.c_void_p),
         ("output_layout", C.c_uint32), ("math_mode", C.c_uint32),
         ("pose_stride_bytes", C.c_uint64),
+        ("skip_mask", C.c_uint32), ("d_skip_track_mask", C.c_void_p), ("d_request_policies", C.c_void_p),
     ]
 
     def __init__(self, **kw):
@@ -112,6 +114,11 @@ def _lib():
         l.aclb200_debug_seek.argtypes = [vp, vp, vp, u32, C.POINTER(Options), vp, vp]
         l.aclb200_debug_unpack.argtypes = [vp, vp, vp, u32, C.POINTER(Options), u32, u32, vp, vp]
         l.aclb200_debug_set_trace.argtypes = [vp, vp, u32, u32]
+        l.aclb200_device_malloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+        l.aclb200_device_free.argtypes = [vp, vp]
+        l.aclb200_device_free.restype = None
+        l.aclb200_copy_to_device.argtypes = [vp, vp, vp, C.c_size_t]
+        l.aclb200_copy_to_host.argtypes = [vp, vp, vp, C.c_size_t]
         l.aclb200_launch_count.argtypes = [vp]
         l.aclb200_launch_count.restype = u64
         _lib_handle = l
@@ -126,6 +133,7 @@ def exported_symbols() -> list[str]:
         "aclb200_clipset_get_info", "aclb200_clipset_get_clip_info", "aclb200_decompress_tracks", "aclb200_decompress_track",
         "aclb200_scalar_decompress_tracks", "aclb200_scalar_decompress_track", "aclb200_decompress_tracks_host",
         "aclb200_debug_seek", "aclb200_debug_unpack", "aclb200_debug_set_trace", "aclb200_launch_count",
+        "aclb200_device_malloc", "aclb200_device_free", "aclb200_copy_to_device", "aclb200_copy_to_host",
     ]
 
 

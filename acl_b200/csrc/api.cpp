@@ -40,6 +40,10 @@ namespace aclb200
 			if (options->rounding_policy == ACLB200_ROUND_PER_TRACK && !options->per_track_rounding)
 				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "per track rounding must be enabled to seek with the per_track policy");
 
+			// the per track rounding kernels read one batch wide seek policy for the tracks that do not override it
+			if (options->d_request_policies != nullptr && options->per_track_rounding)
+				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "per request policies (d_request_policies) need per_track_rounding == 0");
+
 			std::memset(&params, 0, sizeof(params));
 			params.data = clipset->d_data;
 			params.clips = clipset->d_clips;
@@ -76,13 +80,18 @@ namespace aclb200
 			std::memcpy(params.constant_defaults, options->constant_defaults, sizeof(params.constant_defaults));
 			params.variable_defaults = options->d_variable_defaults;
 			params.per_track_policies = options->d_per_track_rounding;
+			params.skip_all = is_transform ? (options->skip_mask & 7u) : 0u;
+			params.skip_tracks = is_transform ? options->d_skip_track_mask : nullptr;
+			params.request_policies = options->d_request_policies;
 			params.layout = options->output_layout;
 			// `skipped` default sub-tracks must keep what the caller's buffer holds: those launches store sub-tracks straight to
 			// global memory instead of assembling whole poses in shared memory
 			const bool any_skipped = options->default_rotation_mode == ACLB200_DEFAULT_SKIPPED || options->default_translation_mode == ACLB200_DEFAULT_SKIPPED
 				|| options->default_scale_mode == ACLB200_DEFAULT_SKIPPED;
+			// ... and so must skipped sub-tracks (track_writer::skip_*)
+			const bool any_masked = (options->skip_mask & 7u) != 0 || options->d_skip_track_mask != nullptr;
 			const bool tracks_launch = is_transform && !single_track;
-			plan_launch(params, tracks_launch ? clipset->max_key_frame_bytes : 0u, context->max_dynamic_smem, tracks_launch && !any_skipped);
+			plan_launch(params, tracks_launch ? clipset->max_key_frame_bytes : 0u, context->max_dynamic_smem, tracks_launch && !any_skipped && !any_masked);
 			return ACLB200_OK;
 		}
 
@@ -261,7 +270,8 @@ extern "C"
 		// leave `skipped` default sub-tracks untouched, or whose poses do not fit in shared memory, use the plain kernels instead.
 		const bool any_skipped = options->default_rotation_mode == ACLB200_DEFAULT_SKIPPED || options->default_translation_mode == ACLB200_DEFAULT_SKIPPED
 			|| options->default_scale_mode == ACLB200_DEFAULT_SKIPPED;
-		if (!any_skipped && clipset->max_key_frame_bytes != 0)
+		const bool any_masked = (options->skip_mask & 7u) != 0 || options->d_skip_track_mask != nullptr;
+		if (!any_skipped && !any_masked && clipset->max_key_frame_bytes != 0)
 		{
 			DecodeParams pipeline_params = params;
 			if (plan_pipeline(pipeline_params, clipset->max_key_frame_bytes, context->max_dynamic_smem, context->num_sms))
@@ -371,7 +381,8 @@ extern "C"
 
 		// `skipped` default sub-tracks keep what the caller's buffer held: bring the buffer in first in that case
 		const bool keeps_input = is_transform && (options->default_rotation_mode == ACLB200_DEFAULT_SKIPPED
-			|| options->default_translation_mode == ACLB200_DEFAULT_SKIPPED || options->default_scale_mode == ACLB200_DEFAULT_SKIPPED);
+			|| options->default_translation_mode == ACLB200_DEFAULT_SKIPPED || options->default_scale_mode == ACLB200_DEFAULT_SKIPPED
+			|| (options->skip_mask & 7u) != 0 || options->d_skip_track_mask != nullptr);
 		// Rows no request writes (clips shorter than the widest one, requests naming a clip outside the set) read as zero. Clearing the
 		// scratch costs a pass over it, so it only happens when such rows can exist.
 		bool needs_clear = !keeps_input && (clipset->info.min_tracks != clipset->info.max_tracks || pose_stride != uint64_t(clipset->info.max_tracks) * bone_stride);
@@ -459,6 +470,39 @@ extern "C"
 		context->trace_blocks = d_trace != nullptr ? num_blocks : 0;
 		context->trace_iterations = d_trace != nullptr ? num_iterations : 0;
 		return ACLB200_OK;
+	}
+
+	aclb200_status aclb200_device_malloc(aclb200_context* context, size_t bytes, void** out_device_pointer)
+	{
+		if (context == nullptr || out_device_pointer == nullptr)
+			return ACLB200_ERR_INVALID_ARGUMENT;
+		*out_device_pointer = nullptr;
+		cudaSetDevice(context->device);
+		return check_cuda(context, cudaMalloc(out_device_pointer, bytes == 0 ? 1 : bytes), "device_malloc");
+	}
+
+	void aclb200_device_free(aclb200_context* context, void* device_pointer)
+	{
+		if (context == nullptr || device_pointer == nullptr)
+			return;
+		cudaSetDevice(context->device);
+		cudaFree(device_pointer);
+	}
+
+	aclb200_status aclb200_copy_to_device(aclb200_context* context, void* device_destination, const void* host_source, size_t bytes)
+	{
+		if (context == nullptr || (bytes != 0 && (device_destination == nullptr || host_source == nullptr)))
+			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "copy_to_device: null pointer");
+		cudaSetDevice(context->device);
+		return check_cuda(context, cudaMemcpy(device_destination, host_source, bytes, cudaMemcpyHostToDevice), "copy_to_device");
+	}
+
+	aclb200_status aclb200_copy_to_host(aclb200_context* context, void* host_destination, const void* device_source, size_t bytes)
+	{
+		if (context == nullptr || (bytes != 0 && (host_destination == nullptr || device_source == nullptr)))
+			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "copy_to_host: null pointer");
+		cudaSetDevice(context->device);
+		return check_cuda(context, cudaMemcpy(host_destination, device_source, bytes, cudaMemcpyDeviceToHost), "copy_to_host");
 	}
 
 	uint64_t aclb200_launch_count(const aclb200_context* context)

@@ -129,6 +129,9 @@ namespace aclb200
 		float    constant_defaults[12];
 		const float* variable_defaults;
 		const uint8_t* per_track_policies;
+		uint32_t skip_all;					// ACLB200_SKIP_* bits skipped for every track
+		const uint8_t* skip_tracks;			// [max_tracks] ACLB200_SKIP_* bits per track, or nullptr
+		const uint8_t* request_policies;	// [num_requests][2] { rounding, looping } per request, or nullptr
 		uint32_t layout;
 		uint32_t debug_which;
 		uint32_t debug_max_sub_tracks;

@@ -127,15 +127,38 @@ namespace aclb200
 		}
 
 		// Looping policy + clamp duration: initialize_v0 / set_looping_policy_v0, decompression.transform.h:120-129,186-204
-		__device__ __forceinline__ void resolve_looping(const DecodeParams& p, const ClipDesc& clip, uint32_t& policy, float& duration)
+		__device__ __forceinline__ void resolve_looping(const DecodeParams& p, const ClipDesc& clip, uint32_t requested, uint32_t& policy, float& duration)
 		{
 			if (!p.wrapping)
 				policy = ACLB200_LOOP_CLAMP;
-			else if (p.looping_policy == ACLB200_LOOP_AS_COMPRESSED)
+			else if (requested == ACLB200_LOOP_AS_COMPRESSED)
 				policy = (clip.flags & k_clip_wrap) ? ACLB200_LOOP_WRAP : ACLB200_LOOP_CLAMP;
 			else
-				policy = p.looping_policy;
+				policy = requested;
 			duration = policy == ACLB200_LOOP_WRAP ? clip.duration_wrap : clip.duration_clamp;
+		}
+
+		// seek(sample_time, rounding_policy) and set_looping_policy(policy) of one request: the batch wide options, or the request's
+		// own pair (aclb200_options::d_request_policies)
+		__device__ __forceinline__ void request_policies(const DecodeParams& p, uint32_t request_index, uint32_t& rounding, uint32_t& looping)
+		{
+			rounding = p.rounding_policy;
+			looping = p.looping_policy;
+			if (p.request_policies != nullptr)
+			{
+				const uint32_t pair = __ldg(reinterpret_cast<const unsigned short*>(p.request_policies) + request_index);
+				rounding = (pair & 0xFFu) <= ACLB200_ROUND_NEAREST ? (pair & 0xFFu) : ACLB200_ROUND_NONE;
+				looping = (pair >> 8) <= ACLB200_LOOP_AS_COMPRESSED ? (pair >> 8) : ACLB200_LOOP_AS_COMPRESSED;
+			}
+		}
+
+		// track_writer::skip_all_*() || skip_track_*(track), core/track_writer.h:181-191 (kind 0 rotation, 1 translation, 2 scale)
+		__device__ __forceinline__ bool skip_sub_track(const DecodeParams& p, uint32_t kind, uint32_t track)
+		{
+			uint32_t bits = p.skip_all;
+			if (p.skip_tracks != nullptr)
+				bits |= __ldg(p.skip_tracks + track);
+			return ((bits >> kind) & 1u) != 0;
 		}
 
 		// find_linear_interpolation_samples_with_sample_rate, core/impl/interpolation_utils.impl.h:143-201
@@ -177,9 +200,10 @@ namespace aclb200
 
 			const uint8_t* image = p.data + clip.data_offset;
 
-			uint32_t looping_policy;
+			uint32_t rounding_policy, requested_looping, looping_policy;
 			float duration;
-			resolve_looping(p, clip, looping_policy, duration);
+			request_policies(p, request_index, rounding_policy, requested_looping);
+			resolve_looping(p, clip, requested_looping, looping_policy, duration);
 
 			float sample_time = request.sample_time;
 			if (p.clamp_sample_time)
@@ -187,7 +211,7 @@ namespace aclb200
 
 			uint32_t key_frame0, key_frame1;
 			float alpha;
-			find_key_frames(clip.num_samples, clip.sample_rate, sample_time, p.rounding_policy, looping_policy, key_frame0, key_frame1, alpha);
+			find_key_frames(clip.num_samples, clip.sample_rate, sample_time, rounding_policy, looping_policy, key_frame0, key_frame1, alpha);
 
 			const SegDesc* segs = reinterpret_cast<const SegDesc*>(image + clip.seg_table_offset);
 			const bool stripped = (clip.flags & k_clip_stripped) != 0;
@@ -727,7 +751,10 @@ namespace aclb200
 				const uint32_t type = uint32_t(desc) & 3;
 				const uint32_t rank = (uint32_t(desc) >> 2) & k_bone_index_mask;
 				float q[4];
-				if (type == 0)
+				if (skip_sub_track(p, 0, bone))
+				{
+				}
+				else if (type == 0)
 				{
 					if (default_value(p, 0, bone, rs.clip_flags, q))
 						write_rotation(p.layout, out_bone, q);
@@ -759,6 +786,8 @@ namespace aclb200
 				const uint32_t type = (kind == 2 && !(rs.clip_flags & k_clip_has_scale)) ? 0u : (bits & 3);
 				const uint32_t rank = (bits >> 2) & k_bone_index_mask;
 				float v[4];
+				if (skip_sub_track(p, kind, bone))
+					continue;
 				if (type == 0)
 				{
 					if (default_value(p, kind, bone, rs.clip_flags, v))

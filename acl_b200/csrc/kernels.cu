@@ -126,6 +126,8 @@ namespace aclb200
 						continue;
 					float rotation[4];
 					const uint32_t bone = animated_rotation<NORM, PER_TRACK, false, STAGED>(p, rs, s_stage, rank, rs.alpha, rotation);
+					if (skip_sub_track(p, 0, bone))
+						continue;
 					uint8_t* pose = OUT_STAGED ? s_out + size_t(local_request) * p.smem_pose_bytes : rs.out;
 					write_rotation(p.layout, pose + size_t(bone) * p.bone_stride, rotation);
 				}
@@ -151,6 +153,8 @@ namespace aclb200
 						continue;
 					float value[3];
 					const uint32_t bone = animated_vector<PER_TRACK, false, STAGED>(p, rs, s_stage, kind, rank, rs.alpha, value);
+					if (skip_sub_track(p, kind, bone))
+						continue;
 					uint8_t* pose = OUT_STAGED ? s_out + size_t(local_request) * p.smem_pose_bytes : rs.out;
 					write_vector(p.layout, pose + size_t(bone) * p.bone_stride, kind, value);
 				}
@@ -200,7 +204,7 @@ namespace aclb200
 			const uint64_t desc = __ldg(reinterpret_cast<const unsigned long long*>(rs.image + rs.bone_table_off) + bone);
 			constant_sub_tracks<NORM, true>(p, rs, bone, desc, out_bone);
 
-			if ((uint32_t(desc) & 3) == 2)
+			if ((uint32_t(desc) & 3) == 2 && !skip_sub_track(p, 0, bone))
 			{
 				float rotation[4];
 				animated_rotation<NORM, PER_TRACK, true, false>(p, rs, nullptr, (uint32_t(desc) >> 2) & k_bone_index_mask, rs.alpha, rotation);
@@ -210,7 +214,7 @@ namespace aclb200
 			for (uint32_t kind = 1; kind <= 2; ++kind)
 			{
 				const uint32_t bits = uint32_t(desc >> (k_bone_kind_shift * kind));
-				if ((bits & 3) == 2 && (kind == 1 || (rs.clip_flags & k_clip_has_scale)))
+				if ((bits & 3) == 2 && (kind == 1 || (rs.clip_flags & k_clip_has_scale)) && !skip_sub_track(p, kind, bone))
 				{
 					float value[3];
 					animated_vector<PER_TRACK, true, false>(p, rs, nullptr, kind, (bits >> 2) & k_bone_index_mask, rs.alpha, value);
@@ -297,16 +301,17 @@ namespace aclb200
 			if (clip.num_tracks == 0 || clip.num_samples == 0)
 				return;
 
-			uint32_t looping_policy;
+			uint32_t rounding_policy, requested_looping, looping_policy;
 			float duration;
-			resolve_looping(p, clip, looping_policy, duration);
+			request_policies(p, request_index, rounding_policy, requested_looping);
+			resolve_looping(p, clip, requested_looping, looping_policy, duration);
 			float sample_time = request.sample_time;
 			if (p.clamp_sample_time)
 				sample_time = fminf(fmaxf(sample_time, 0.0f), duration);
 
 			uint32_t key_frame0, key_frame1;
 			float alpha;
-			find_key_frames(clip.num_samples, clip.sample_rate, sample_time, p.rounding_policy, looping_policy, key_frame0, key_frame1, alpha);
+			find_key_frames(clip.num_samples, clip.sample_rate, sample_time, rounding_policy, looping_policy, key_frame0, key_frame1, alpha);
 
 			rs.image = p.data + clip.data_offset;
 			rs.tracks = reinterpret_cast<const ScalarTrackDesc*>(rs.image + clip.bone_table_offset);

@@ -32,7 +32,7 @@ extern "C" {
 #endif
 
 #define ACLB200_VERSION_MAJOR 0
-#define ACLB200_VERSION_MINOR 1
+#define ACLB200_VERSION_MINOR 2
 
 typedef enum aclb200_status
 {
@@ -116,7 +116,21 @@ typedef struct aclb200_options
 	uint32_t output_layout;					/* ACLB200_LAYOUT_* */
 	uint32_t math_mode;						/* ACLB200_MATH_* */
 	uint64_t pose_stride_bytes;				/* distance between the poses of consecutive requests; 0 = max_tracks * bone size */
+
+	/* track_writer::skip_all_rotations/translations/scales() and skip_track_rotation/translation/scale(track)
+	 * (core/track_writer.h:181-191, honoured per sub-track at decompression.transform.h:626-665 and in every unpack pass):
+	 * a skipped sub-track is NOT written, the output buffer keeps what it held. Transform clip sets only. */
+	uint32_t skip_mask;						/* ACLB200_SKIP_* bits: sub-track kinds skipped for every track */
+	const uint8_t* d_skip_track_mask;		/* device [max_tracks] bytes of ACLB200_SKIP_* bits: sub-tracks skipped per track, or NULL */
+
+	/* seek(sample_time, rounding_policy) / set_looping_policy(policy) PER REQUEST (the reference takes both per call,
+	 * decompress.h:147-160): device [num_requests][2] bytes { ACLB200_ROUND_* (none..nearest), ACLB200_LOOP_* }, or NULL to use
+	 * rounding_policy / looping_policy above for the whole batch. Values out of range read as none / as_compressed;
+	 * ACLB200_ROUND_PER_TRACK stays a batch wide choice (rounding_policy + d_per_track_rounding). */
+	const uint8_t* d_request_policies;
 } aclb200_options;
+
+enum { ACLB200_SKIP_ROTATION = 1, ACLB200_SKIP_TRANSLATION = 2, ACLB200_SKIP_SCALE = 4 };
 
 typedef struct aclb200_clipset_info
 {
@@ -235,6 +249,13 @@ ACLB200_API aclb200_status aclb200_debug_unpack(aclb200_context* context, const 
  * `num_blocks` blocks record 8 clock64() stamps per batch they decode, for their first `num_iterations` batches, at
  * d_trace[(block * num_iterations + iteration) * 8 + k] (uint64). NULL switches it off. tools/pipe_trace.py reads it. */
 ACLB200_API aclb200_status aclb200_debug_set_trace(aclb200_context* context, void* d_trace, uint32_t num_blocks, uint32_t num_iterations);
+
+/* Plain device memory helpers so that a host language without the CUDA runtime can hand device arrays (requests, variable
+ * defaults, per track policies, skip masks, outputs) to the entry points above. Synchronous. */
+ACLB200_API aclb200_status aclb200_device_malloc(aclb200_context* context, size_t bytes, void** out_device_pointer);
+ACLB200_API void aclb200_device_free(aclb200_context* context, void* device_pointer);
+ACLB200_API aclb200_status aclb200_copy_to_device(aclb200_context* context, void* device_destination, const void* host_source, size_t bytes);
+ACLB200_API aclb200_status aclb200_copy_to_host(aclb200_context* context, void* host_destination, const void* device_source, size_t bytes);
 
 /* Number of kernels launched by this context so far (bench.py reports it as `gpu_launches`). */
 ACLB200_API uint64_t aclb200_launch_count(const aclb200_context* context);

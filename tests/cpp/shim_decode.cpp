@@ -1,5 +1,7 @@
 // tests/cpp/shim_decode.cpp -- exercises include/acl_b200/decompress.h the way a reference call site would be written.
-// usage: shim_decode <clip.acl.bin> <t0> [t1 ...]   prints one line per (time, track): 12 floats as hex words.
+// usage: shim_decode <clip.acl.bin> <default|debug> <t0> [t1 ...]   prints one line per (time, track): 12 floats as hex words.
+// (settings: acl's default_transform_decompression_settings only support the variable formats, like the reference's; clips in
+// full precision formats need the debug settings)
 // Exit code 3 when no usable GPU exists (the library has no CPU fallback), so the CPU-side test can check exactly that.
 #include "../../include/acl_b200/decompress.h"
 
@@ -20,18 +22,29 @@ namespace
 	};
 }
 
+template<class settings_type>
+int run(const std::vector<char>& blob, int argc, char** argv);
+
 int main(int argc, char** argv)
 {
-	if (argc < 3)
+	if (argc < 4)
 		return 2;
 	std::ifstream file(argv[1], std::ios::binary);
 	std::vector<char> blob((std::istreambuf_iterator<char>(file)), std::istreambuf_iterator<char>());
 	if (blob.empty())
 		return 2;
+	if (std::string(argv[2]) == "debug")
+		return run<acl_b200::debug_transform_decompression_settings>(blob, argc, argv);
+	return run<acl_b200::default_transform_decompression_settings>(blob, argc, argv);
+}
+
+template<class settings_type>
+int run(const std::vector<char>& blob, int argc, char** argv)
+{
 	try
 	{
 		acl_b200::device_context device(0);
-		acl_b200::decompression_context<acl_b200::default_transform_decompression_settings> context(device);
+		acl_b200::decompression_context<settings_type> context(device);
 		if (!context.initialize(blob.data(), uint32_t(blob.size())))
 		{
 			std::printf("initialize failed\n");
@@ -39,14 +52,14 @@ int main(int argc, char** argv)
 		}
 		uint32_t num_tracks = 0;
 		std::memcpy(&num_tracks, blob.data() + 16, 4);		// tracks_header::num_tracks
-		for (int i = 2; i < argc; ++i)
+		for (int i = 3; i < argc; ++i)
 		{
 			pose_writer writer(num_tracks);
 			context.seek(float(std::atof(argv[i])), acl_b200::sample_rounding_policy::none);
 			context.decompress_tracks(writer);
 			for (uint32_t track = 0; track < num_tracks; ++track)
 			{
-				std::printf("%d %u", i - 2, track);
+				std::printf("%d %u", i - 3, track);
 				for (int c = 0; c < 12; ++c)
 				{
 					uint32_t bits;

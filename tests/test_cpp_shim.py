@@ -27,7 +27,7 @@ def test_shim_compiles_and_has_no_cpu_fallback(tmp_path):
     """The shim is plain C++14 over the C ABI; without a GPU the program must fail with NO_DEVICE, not decode on the CPU."""
     import torch
     exe = build_shim_program(tmp_path)
-    result = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "c1_30bones.acl.bin"), "0.1"], capture_output=True, text=True)
+    result = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "c1_30bones.acl.bin"), "default", "0.1"], capture_output=True, text=True)
     if torch.cuda.is_available():
         assert result.returncode == 0
     else:
@@ -42,10 +42,13 @@ def test_shim_decode_matches_oracle(tmp_path, oracle_port, name):
     exe = build_shim_program(tmp_path)
     blob = clips.load_blob(name)
     times = [float(t) for t in clips.sample_times(clips.TRANSFORM_SPECS[name])[::2]]
-    result = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", name + ".acl.bin")] + [repr(t) for t in times],
+    # the default settings only support the variable formats (decompression_settings.h:211-232), like the reference's: the full
+    # precision clip goes through the debug settings (oracle kind 1)
+    debug = name == "full_formats"
+    result = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", name + ".acl.bin"), "debug" if debug else "default"] + [repr(t) for t in times],
                             capture_output=True, text=True, check=True)
     rows = [line.split() for line in result.stdout.strip().splitlines()]
-    settings = oracle_port.settings_for_kind(0)
+    settings = oracle_port.settings_for_kind(1 if debug else 0)
     num_tracks = max(int(r[1]) for r in rows) + 1
     got = np.zeros((len(times), num_tracks, 12), np.uint32)
     for r in rows:
@@ -84,3 +87,54 @@ def test_batch_context_matches_oracle(tmp_path, oracle_port):
         n = expected.shape[0]
         assert np.array_equal(expected[:, clips.DEFINED_LANES].view(np.uint32), got[i][:n][:, clips.DEFINED_LANES]), (names[c], t)
         assert not got[i][n:].any()       # bones past the clip's own track count are left untouched
+
+
+REFERENCE_INCLUDES = ["/root/reference/includes", "/root/reference/external/rtm/includes"]
+CALLSITE_EXE = os.path.join(ROOT, "tests", "cpp", "_build", "shim_reference_callsite")
+
+
+def build_reference_callsite():
+    """tests/cpp/shim_reference_callsite.cpp needs the reference's headers: it is built where /root/reference exists
+    (__graft_entry__.build() does it too) and travels to the GPU box prebuilt, like oracle/_ref."""
+    os.makedirs(os.path.dirname(CALLSITE_EXE), exist_ok=True)
+    cmd = ["g++", "-std=c++14", "-O2", "-msse4.1", "-ffp-contract=off", "-Wall", "-Wextra"] + ["-I" + d for d in REFERENCE_INCLUDES] + [
+        "-o", CALLSITE_EXE, os.path.join(ROOT, "tests", "cpp", "shim_reference_callsite.cpp"),
+        "-L" + os.path.join(ROOT, "acl_b200"), "-laclb200", "-Wl,-rpath,$ORIGIN/../../../acl_b200"]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+
+
+@pytest.mark.skipif(not all(os.path.isdir(d) for d in REFERENCE_INCLUDES), reason="needs the reference's headers")
+def test_reference_callsite_compiles_against_the_shim():
+    """The reference's own benchmark loop body (benchmark.cpp:246-258) with acl::debug_track_writer, acl::compressed_tracks, settings
+    derived from acl::default_transform_decompression_settings: instantiated with acl::decompression_context and with
+    acl_b200::decompression_context. Without a GPU the program must stop with NO_DEVICE (no CPU fallback)."""
+    import torch
+    build_reference_callsite()
+    result = subprocess.run([CALLSITE_EXE, os.path.join(ROOT, "tests", "golden", "c1_30bones.acl.bin")], capture_output=True, text=True)
+    if not torch.cuda.is_available():
+        assert result.returncode == 3, (result.returncode, result.stdout, result.stderr)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c1_30bones", "c2_100bones", "mixed_scale", "stripped_loop", "float1", "float3", "vector4"])
+def test_reference_callsite_matches_the_reference(name):
+    """Same call site, both classes, on the GPU box (prebuilt binary): decompress_tracks bit-identical, decompress_track rotations
+    within 1e-5, relocated / is_bound_to / initialize answer like the reference."""
+    if not os.path.exists(CALLSITE_EXE):
+        pytest.skip("tests/cpp/_build/shim_reference_callsite was not built (needs /root/reference at build time)")
+    result = subprocess.run([CALLSITE_EXE, os.path.join(ROOT, "tests", "golden", name + ".acl.bin"), os.path.join(ROOT, "tests", "golden", "ragged_17.acl.bin")],
+                            capture_output=True, text=True)
+    assert result.returncode == 0 and "PASS" in result.stdout, (result.stdout, result.stderr)
+
+
+def test_binding_shim_compiles(tmp_path):
+    build_shim_program(tmp_path, "shim_binding")
+
+
+@pytest.mark.gpu
+def test_binding_semantics_follow_the_reference(tmp_path):
+    """relocated() compares hashes, is_bound_to() address + hash, failed initialize leaves the context unbound."""
+    exe = build_shim_program(tmp_path, "shim_binding")
+    golden = os.path.join(ROOT, "tests", "golden")
+    result = subprocess.run([exe, os.path.join(golden, "c1_30bones.acl.bin"), os.path.join(golden, "mixed_scale.acl.bin")], capture_output=True, text=True)
+    assert result.returncode == 0 and "PASS" in result.stdout, (result.stdout, result.stderr)

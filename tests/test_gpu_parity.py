@@ -462,3 +462,56 @@ def test_full_size_c2_properties(gpu, c2_full):
         blob = w["buffer"][int(w["offsets"][clip]):int(w["offsets"][clip]) + int(w["sizes"][clip])]
         want = port.transform_decompress_tracks(blob, settings, float(w["req_time"][r]))
         assert clips.bit_equal(got[j], want[:, LANES]), (int(r), clip)
+
+
+def test_skip_masks_leave_sub_tracks_untouched(gpu):
+    """track_writer::skip_all_*() / skip_track_*(track) (core/track_writer.h:181-191): a skipped sub-track is not written --
+    the caller's buffer keeps its bytes -- everything else is bit-exact."""
+    port, ab, ctx, torch = gpu["port"], gpu["ab"], gpu["ctx"], gpu["torch"]
+    name = "mixed_scale"
+    spec, blob = clips.TRANSFORM_SPECS[name], clips.load_blob(name)
+    clipset = ctx.upload([blob], check_hash=True)
+    times = clips.sample_times(spec)
+    n = clipset.max_tracks
+    settings = port.settings_for_kind(0)
+    rng = np.random.default_rng(4)
+    per_track = rng.integers(0, 8, size=n).astype(np.uint8)
+    d_per_track = _to_device(gpu, per_track)
+    marker = np.float32(-12345.5)
+    lane_kind = {0: 0, 1: 0, 2: 0, 3: 0, 4: 1, 5: 1, 6: 1, 8: 2, 9: 2, 10: 2}
+    for skip_all, use_tracks in ((ab.SKIP_ROTATION, False), (ab.SKIP_TRANSLATION | ab.SKIP_SCALE, False), (0, True), (ab.SKIP_SCALE, True)):
+        options = _options(gpu, settings, skip_mask=skip_all, d_skip_track_mask=d_per_track.data_ptr() if use_tracks else None)
+        prefill = np.full((len(times), n, 12), marker, dtype=np.float32)
+        got = _decode(gpu, clipset, np.zeros(len(times), np.uint32), times, options, prefill=prefill)
+        for i, t in enumerate(times):
+            want = port.transform_decompress_tracks(blob, settings, float(t))
+            for track in range(n):
+                bits = skip_all | (int(per_track[track]) if use_tracks else 0)
+                for lane in LANES:
+                    if (bits >> lane_kind[lane]) & 1:
+                        assert got[i, track, lane] == marker, (skip_all, use_tracks, track, lane)
+                    else:
+                        assert got[i, track, lane].view(np.uint32) == want[track, lane].view(np.uint32), (skip_all, use_tracks, float(t), track, lane)
+    clipset.release()
+
+
+def test_per_request_rounding_and_looping(gpu):
+    """seek(t, rounding) + set_looping_policy(policy) per request (decompress.h:147-160): one launch mixing every pair equals the
+    per policy launches."""
+    port, ab, ctx = gpu["port"], gpu["ab"], gpu["ctx"]
+    names = ["looping", "stripped_loop", "c1_30bones", "mixed_scale"]
+    blobs = [clips.load_blob(nm) for nm in names]
+    clipset = ctx.upload(blobs, check_hash=True)
+    rng = np.random.default_rng(6)
+    count = 240
+    req_clip = rng.integers(0, len(names), count).astype(np.uint32)
+    req_time = np.array([rng.uniform(-0.2, (clips.TRANSFORM_SPECS[names[c]].num_samples + 2) / 30.0) for c in req_clip], dtype=np.float32)
+    policies = np.stack([rng.integers(0, 4, count), rng.integers(0, 3, count)], axis=1).astype(np.uint8)
+    settings = port.settings_for_kind(0)
+    d_policies = _to_device(gpu, policies)
+    got = _decode(gpu, clipset, req_clip, req_time, _options(gpu, settings, d_request_policies=d_policies.data_ptr()))
+    for i in range(count):
+        want = port.transform_decompress_tracks(blobs[req_clip[i]], settings, float(req_time[i]), int(policies[i, 0]), int(policies[i, 1]))
+        nt = want.shape[0]
+        assert clips.bit_equal(got[i, :nt][:, LANES], want[:, LANES]), (i, names[req_clip[i]], float(req_time[i]), policies[i].tolist())
+    clipset.release()
