@@ -282,7 +282,9 @@ extern "C"
 				pipeline_params.trace_blocks = context->trace_blocks;
 				pipeline_params.trace_iterations = context->trace_iterations;
 				acquire_base_poses(clipset, pipeline_params, static_cast<cudaStream_t>(stream));
-				return finish_launch(context, launch_transform_pipeline(pipeline_params, options->math_mode, static_cast<cudaStream_t>(stream)), "decompress_tracks (pipeline)");
+				const cudaError_t launched = launch_transform_pipeline(pipeline_params, options->math_mode, static_cast<cudaStream_t>(stream));
+				release_base_poses_use(clipset, pipeline_params, static_cast<cudaStream_t>(stream));
+				return finish_launch(context, launched, "decompress_tracks (pipeline)");
 			}
 		}
 		return finish_launch(context, launch_transform_decompress_tracks(params, options->math_mode, static_cast<cudaStream_t>(stream)), "decompress_tracks");

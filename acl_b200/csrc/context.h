@@ -51,6 +51,8 @@ namespace aclb200
 		uint8_t* d_rows = nullptr;			// [num_clips][row_stride]
 		uint32_t row_stride = 0;
 		cudaEvent_t ready = nullptr;		// recorded after the build kernel on the stream that asked for it first
+		cudaEvent_t last_launch = nullptr;	// recorded after the latest launch that reads the rows
+		uint32_t users = 0;					// launches being set up with these rows (between acquire and release)
 		uint64_t last_use = 0;
 	};
 }
@@ -152,5 +154,6 @@ namespace aclb200
 	bool plan_pipeline(DecodeParams& params, uint32_t max_key_frame_bytes, int max_dynamic_smem, int num_sms);
 	cudaError_t launch_transform_pipeline(const DecodeParams& params, uint32_t math_mode, cudaStream_t stream);
 	void acquire_base_poses(const aclb200_clipset* clipset, DecodeParams& params, cudaStream_t stream);
+	void release_base_poses_use(const aclb200_clipset* clipset, const DecodeParams& params, cudaStream_t stream);
 	void release_base_poses(aclb200_clipset* clipset);
 }

@@ -107,3 +107,133 @@ def test_bench_workload_c4_every_request_vs_reference(env):
         d_want = torch.from_numpy(np.ascontiguousarray(want)).cuda()
         assert torch.equal(d_out[begin:end].view(torch.int32), d_want.view(torch.int32)), f"requests {begin}..{end}"
     clipset.release()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# v02_00_00 clips: the raw bit rate marker is 32 instead of 31 (animated_track_cache.transform.h:523), scalar tracks use the 19 entry
+# bit rate table (decompression.scalar.h:259-263), the wrap flag does not exist (compressed_tracks.impl.h:127-134). The compressor
+# here only writes the latest version: the fixtures are golden blobs re-labelled on the host (version field, markers / table
+# indices re-mapped so that the payload means the same, hash recomputed) and decoded by the unmodified reference.
+# ------------------------------------------------------------------------------------------------------------------
+def _fnv1a32(data: np.ndarray) -> int:
+    acc = 2166136261
+    for byte in data.tobytes():
+        acc = ((acc ^ byte) * 16777619) & 0xFFFFFFFF
+    return acc
+
+
+def _as_version_7(blob: np.ndarray):
+    """Returns (re-labelled blob, number of raw / re-mapped entries), or None when the clip cannot be expressed in v02_00_00."""
+    b = blob.copy()
+    u32 = lambda off: int(b[off:off + 4].view(np.uint32)[0])
+    size = u32(0)
+    track_type, misc = int(b[15]), u32(28)
+    touched = 0
+    if track_type == 12:
+        if (misc >> 10) & 1 or (misc >> 30) & 1:
+            return None                                  # stripped key frames / wrap optimised loops do not exist in v02_00_00
+        num_segments, num_variable = u32(32), u32(36)
+        headers = 32 + u32(32 + 36)
+        for s in range(num_segments):
+            data = 32 + u32(headers + 16 * s + 12)
+            fmt = b[data:data + num_variable]
+            touched += int((fmt == 31).sum())
+            fmt[fmt == 31] = 32
+    else:
+        v10 = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 32]
+        v7 = [0, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 32]
+        num_tracks = u32(16)
+        meta = 32 + u32(32 + 4)
+        rates = b[meta:meta + num_tracks]
+        bits = [v10[r] for r in rates]
+        if any(x not in v7 for x in bits):
+            return None
+        rates[:] = [v7.index(x) for x in bits]
+        touched = num_tracks
+    b[12:14] = np.array([7], dtype=np.uint16).view(np.uint8)
+    b[4:8] = np.array([_fnv1a32(b[8:size])], dtype=np.uint32).view(np.uint8)
+    return b, touched
+
+
+@pytest.mark.parametrize("name", ["noisy_raw", "mixed_scale", "c1_30bones", "full_formats"])
+def test_v02_00_00_transform_clip_vs_reference(env, name):
+    torch, ab, ref, ctx = env["torch"], env["ab"], env["ref"], env["ctx"]
+    made = _as_version_7(clips.load_blob(name))
+    assert made is not None
+    blob, raw_entries = made
+    blob = ref.aligned_blob(blob)
+    assert ref.lib().aclref_is_valid(blob.ctypes.data, 1) == 0, "the reference itself must accept the re-labelled clip (hash checked)"
+    if name == "noisy_raw":
+        assert raw_entries > 0, "this clip is here for its raw bit rate sub-tracks"
+    clipset = ctx.upload([blob], check_hash=True)
+    spec = clips.TRANSFORM_SPECS[name]
+    times = clips.sample_times(spec)
+    requests = ab.make_requests(np.zeros(len(times), np.uint32), times)
+    d_requests = torch.from_numpy(requests.view(np.uint8)).cuda()
+    d_out = torch.full((len(times), clipset.max_tracks, 12), float("nan"), dtype=torch.float32, device="cuda")
+    # debug settings: every format, version `any`, rotations always normalised
+    options = ab.Options(normalization=ab.NORMALIZE_ALWAYS, per_track_rounding=1, multiple_rotation_formats=1,
+                         default_modes=(ab.DEFAULT_CONSTANT, ab.DEFAULT_CONSTANT, ab.DEFAULT_LEGACY))
+    ctx.decompress_tracks(clipset, d_requests, len(times), options, d_out)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    for i, t in enumerate(times):
+        want = ref.decompress_tracks(blob, float(t), settings=ref.SETTINGS_DEBUG, writer=ref.WRITER_LEGACY)
+        assert clips.bit_equal(got[i][:, LANES], want[:, LANES]), (name, float(t))
+    clipset.release()
+
+
+@pytest.mark.parametrize("name", ["float1", "float3", "vector4"])
+def test_v02_00_00_scalar_clip_vs_reference(env, name):
+    torch, ab, ref, ctx = env["torch"], env["ab"], env["ref"], env["ctx"]
+    made = _as_version_7(clips.load_blob(name))
+    if made is None:
+        pytest.skip("this clip uses bit rates the v02_00_00 table does not have")
+    blob = ref.aligned_blob(made[0])
+    assert ref.lib().aclref_is_valid(blob.ctypes.data, 1) == 0
+    clipset = ctx.upload([blob], check_hash=True)
+    spec = clips.SCALAR_SPECS[name]
+    times = clips.sample_times(spec)
+    requests = ab.make_requests(np.zeros(len(times), np.uint32), times)
+    d_requests = torch.from_numpy(requests.view(np.uint8)).cuda()
+    d_out = torch.full((len(times), clipset.max_tracks, clipset.components), float("nan"), dtype=torch.float32, device="cuda")
+    ctx.scalar_decompress_tracks(clipset, d_requests, len(times), ab.Options(), d_out)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    for i, t in enumerate(times):
+        want = ref.scalar_decompress(blob, float(t))
+        assert clips.bit_equal(got[i], want[:, :clipset.components]), (name, float(t))
+    clipset.release()
+
+
+def test_routed_c5_job_matches_reference_per_shard(env):
+    """bench.py's routed C5 job on one GPU: the clip table is split with partition_clips, every shard becomes its own clip
+    set, the global request list is bucketed with route_requests, each shard decodes its requests, and every pose is compared with
+    the reference decoding the ORIGINAL (global) request. What N ranks do, shard after shard."""
+    import bench
+    from acl_b200 import sharding
+    torch, ab, ref, ctx = env["torch"], env["ab"], env["ref"], env["ctx"]
+    w = bench.make_workload("c5", 0, 3000)
+    sizes = w["sizes"].astype(np.int64)
+    blobs = _blobs(w)
+    world = 3
+    owner, local_index, bounds = sharding.partition_clips(sizes, world)
+    rng = np.random.default_rng(11)
+    req_clip = rng.permutation(len(blobs)).astype(np.uint32)
+    req_time = (rng.random(len(blobs)) * (31 / 30.0)).astype(np.float32)
+    want = ref.decode_requests(blobs, req_clip, req_time, 30)
+    seen = 0
+    for rank in range(world):
+        lo, hi = bounds[rank]
+        clipset = ctx.upload(blobs[lo:hi], check_hash=True)
+        positions, local_clip, times = sharding.route_requests(req_clip, req_time, owner, local_index, rank)
+        requests = ab.make_requests(local_clip, times)
+        d_requests = torch.from_numpy(requests.view(np.uint8)).cuda()
+        d_out = torch.zeros((len(requests), 30, 12), dtype=torch.float32, device="cuda")
+        ctx.decompress_tracks(clipset, d_requests, len(requests), ab.Options(), d_out)
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy()
+        assert clips.bit_equal(got[:, :, LANES], want[positions][:, :, LANES]), rank
+        seen += len(positions)
+        clipset.release()
+    assert seen == len(req_clip)
