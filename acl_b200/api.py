@@ -28,6 +28,13 @@ SEEK_STATE_DTYPE = np.dtype([
 ])
 
 
+# numpy views of aclb200_error_job / aclb200_track_error
+ERROR_JOB_DTYPE = np.dtype([("clip", np.uint32), ("num_samples", np.uint32), ("sample_rate", np.float32), ("duration", np.float32),
+                            ("num_tracks", np.uint32), ("skeleton_offset", np.uint32), ("first_raw_pose", np.uint64)])
+TRACK_ERROR_DTYPE = np.dtype([("index", np.uint32), ("error", np.float32), ("sample_time", np.float32), ("flags", np.uint32)])
+ERROR_FLAG_NEGATIVE_SCALE, ERROR_FLAG_INVALID_SKELETON = 1, 2
+
+
 class AclB200Error(RuntimeError):
     def __init__(self, status: int, message: str):
         super().__init__(f"aclb200 status {status}: {message}")
@@ -119,6 +126,9 @@ def _lib():
         l.aclb200_device_free.restype = None
         l.aclb200_copy_to_device.argtypes = [vp, vp, vp, C.c_size_t]
         l.aclb200_copy_to_host.argtypes = [vp, vp, vp, C.c_size_t]
+        l.aclb200_calculate_compression_error.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, C.POINTER(Options), vp, vp, vp]
+        l.aclb200_set_error_chunk_bytes.argtypes = [vp, u64]
+        l.aclb200_local_to_object_space.argtypes = [vp, vp, vp, u64, u32, u64, vp, vp, vp]
         l.aclb200_launch_count.argtypes = [vp]
         l.aclb200_launch_count.restype = u64
         _lib_handle = l
@@ -134,6 +144,7 @@ def exported_symbols() -> list[str]:
         "aclb200_scalar_decompress_tracks", "aclb200_scalar_decompress_track", "aclb200_decompress_tracks_host",
         "aclb200_debug_seek", "aclb200_debug_unpack", "aclb200_debug_set_trace", "aclb200_launch_count",
         "aclb200_device_malloc", "aclb200_device_free", "aclb200_copy_to_device", "aclb200_copy_to_host",
+        "aclb200_calculate_compression_error", "aclb200_set_error_chunk_bytes", "aclb200_local_to_object_space",
     ]
 
 
@@ -277,6 +288,25 @@ class Context:
 
     def debug_set_trace(self, d_trace, num_blocks: int, num_iterations: int) -> None:
         self._check(_lib().aclb200_debug_set_trace(self._handle, _device_ptr(d_trace), num_blocks, num_iterations))
+
+    # ---- compression error measurement and the object space walk, poses stay on the device ----
+    def calculate_compression_error(self, clipset: ClipSet, jobs: np.ndarray, d_raw_poses, d_parent_indices, d_shell_distances,
+                                    options: Options, d_out_errors, d_output_indices=None, d_out_error_matrix=None, stream=None) -> None:
+        jobs = np.ascontiguousarray(jobs)
+        assert jobs.dtype == ERROR_JOB_DTYPE
+        self._check(_lib().aclb200_calculate_compression_error(
+            self._handle, clipset._handle, jobs.ctypes.data, jobs.shape[0], _device_ptr(d_raw_poses), _device_ptr(d_parent_indices),
+            _device_ptr(d_shell_distances), _device_ptr(d_output_indices), C.byref(options), _device_ptr(d_out_errors),
+            _device_ptr(d_out_error_matrix), _stream_ptr(stream)))
+
+    def set_error_chunk_bytes(self, num_bytes: int) -> None:
+        self._check(_lib().aclb200_set_error_chunk_bytes(self._handle, num_bytes))
+
+    def local_to_object_space(self, d_local_poses, d_object_poses, num_poses: int, num_tracks: int, d_parent_indices,
+                              pose_stride_bytes: int = 0, d_out_flags=None, stream=None) -> None:
+        self._check(_lib().aclb200_local_to_object_space(self._handle, _device_ptr(d_local_poses), _device_ptr(d_object_poses), num_poses,
+                                                         num_tracks, pose_stride_bytes, _device_ptr(d_parent_indices),
+                                                         _device_ptr(d_out_flags), _stream_ptr(stream)))
 
     # ---- host buffers in, host buffers out (the call the C++ header shim uses) ----
     def decompress_tracks_host(self, clipset: ClipSet, requests: np.ndarray, options: Options, out: np.ndarray) -> np.ndarray:

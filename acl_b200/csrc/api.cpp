@@ -187,6 +187,7 @@ extern "C"
 		cudaSetDevice(context->device);
 		cudaFree(context->d_scratch_requests);
 		cudaFree(context->d_scratch_out);
+		cudaFree(context->d_error_scratch);
 		if (context->host_stream != nullptr)
 			cudaStreamDestroy(context->host_stream);
 		if (context->copy_stream != nullptr)

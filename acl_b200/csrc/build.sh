@@ -10,5 +10,5 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
   --fmad=false -Xptxas -v \
   -Xcompiler -fPIC,-fvisibility=hidden,-Wall -shared -cudart static \
   -o "$OUT" \
-  "$HERE/kernels.cu" "$HERE/pipeline.cu" "$HERE/clipset.cpp" "$HERE/api.cpp" "$@"
+  "$HERE/kernels.cu" "$HERE/pipeline.cu" "$HERE/error_metric.cu" "$HERE/clipset.cpp" "$HERE/api.cpp" "$@"
 echo "built $OUT"

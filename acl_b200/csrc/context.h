@@ -28,6 +28,11 @@ struct aclb200_context
 	cudaStream_t copy_stream = nullptr;			// device -> host copies of the host-buffer call overlap the next chunk's decode
 	cudaEvent_t chunk_done[2] = { nullptr, nullptr };
 
+	// aclb200_calculate_compression_error (error_metric.cu): job table, arg max accumulators, requests and the decoded poses of one chunk
+	void* d_error_scratch = nullptr;
+	size_t error_scratch_bytes = 0;
+	uint64_t error_chunk_bytes = 512ull << 20;	// decoded poses per chunk (aclb200_set_error_chunk_bytes)
+
 	// aclb200_debug_set_trace
 	unsigned long long* d_trace = nullptr;
 	uint32_t trace_blocks = 0;
@@ -149,6 +154,8 @@ namespace aclb200
 	cudaError_t launch_scalar_decompress_tracks(const DecodeParams& params, cudaStream_t stream);
 	cudaError_t launch_scalar_decompress_track(const DecodeParams& params, cudaStream_t stream);
 	cudaError_t configure_kernels(int& max_dynamic_smem);
+	// error_metric.cu
+	cudaError_t configure_error_kernels(int optin_limit);
 	// pipeline.cu
 	cudaError_t configure_pipeline_kernels(int optin_limit, int& min_available);
 	bool plan_pipeline(DecodeParams& params, uint32_t max_key_frame_bytes, int max_dynamic_smem, int num_sms);

@@ -1,0 +1,775 @@
+// acl_b200/csrc/error_metric.cu -- SURVEY 8(f1) + 8(f3): the nearest caller of the decode hot path inside ACL, on the device.
+//
+//   * aclb200_calculate_compression_error: acl::calculate_compression_error (includes/acl/compression/impl/track_error.impl.h:400-571
+//     -> calculate_transform_track_error :225-392 / calculate_scalar_track_error :166-223) for MANY clips per call: every sample of every
+//     clip is decoded by the decompress_tracks pipeline (pipeline.cu), taken to object space and measured against the raw pose with the
+//     qvvf_transform_error_metric (includes/acl/compression/transform_error_metrics.h:281-385); one {index, error, sample_time} per clip
+//     comes back, the poses never leave the GPU.
+//   * aclb200_local_to_object_space: qvvf_transform_error_metric::local_to_object_space (transform_error_metrics.h:289-310) as a pose
+//     consumer of its own (the hierarchy walk a skinning / blending stage starts with).
+//
+// Work decomposition: ONE WARP PER POSE. The reference walks a pose bone by bone because a bone needs its parent's object transform; here
+// the warp takes 32 consecutive bones at a time and resolves them in wavefronts: a lane whose parent lies in an earlier chunk -- or was
+// finished by an earlier wavefront of this chunk -- computes, the others wait for the next wavefront (skeletons are shallow and bushy:
+// a handful of wavefronts per chunk). Object transforms live in shared memory as [component][bone] planes so that 32 lanes reading 32
+// different parents hit 32 different banks. Every float operation is the reference's, in its order, never fused (the library is built
+// with --fmad=false); the one exception is rtm::quat_normalize, whose SSE2 code starts from the CPU specific rsqrtss estimate
+// (external/rtm/includes/rtm/quatf.h:917-953) and cannot be reproduced bit for bit by anyone: the IEEE 1 / sqrt stands in for it
+// (the tests' CPU restatement has both; errors agree with the reference within 5e-5 on poses tens of units across, tests/test_gpu_error_metric.py).
+#include "context.h"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace aclb200
+{
+	namespace
+	{
+		constexpr uint32_t k_invalid_track = 0xFFFFFFFFu;			// acl::k_invalid_track_index, core/track_types.h
+		constexpr uint32_t k_object_components = 10;				// rotation xyzw, translation xyz, scale xyz
+
+		// One clip to measure, in processing order (a chunk = a run of jobs whose poses fit the scratch).
+		struct alignas(16) ErrorJobDev
+		{
+			uint32_t clip;
+			uint32_t num_samples;
+			uint32_t num_tracks;
+			uint32_t skeleton_offset;
+			float    sample_rate;
+			float    duration;
+			uint32_t chunk_first_pose;		// first pose of the job inside the chunk's scratch
+			uint32_t job_index;				// slot of the result (the caller's job order)
+			uint64_t first_raw_pose;
+			uint64_t out_pose_base;			// first row of the job in the optional per bone error matrix
+		};
+		static_assert(sizeof(ErrorJobDev) == 48, "ErrorJobDev is 48 bytes");
+
+		struct ErrorParams
+		{
+			const ErrorJobDev* jobs;		// the chunk's jobs
+			uint32_t num_jobs;
+			uint32_t num_poses;				// of the chunk
+			aclb200_request* requests;		// [num_poses] (setup kernel output)
+			uint32_t* pose_jobs;			// [num_poses] index into `jobs`
+			const uint8_t* raw_poses;
+			const uint8_t* lossy_poses;		// chunk scratch, pose p at p * pose_stride
+			uint64_t pose_stride;
+			const uint32_t* parent_indices;
+			const float* shell_distances;
+			const uint32_t* output_indices;	// or nullptr
+			unsigned long long* keys;		// [all jobs] arg max accumulators
+			uint32_t* flags;				// [all jobs]
+			float* error_matrix;			// or nullptr
+			uint32_t error_stride;			// floats per row of the matrix
+			uint32_t plane_stride;			// floats per [component] plane of a warp's object transforms
+			uint32_t components;			// scalar clips
+		};
+
+		// ---- the reference's float operations, spelled out so nothing can be contracted -------------------------------------------
+		__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+		__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+		__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+
+		struct Quat { float x, y, z, w; };
+		struct Vec3 { float x, y, z; };
+		struct Qvv { Quat rotation; Vec3 translation; Vec3 scale; };
+
+		// rtm::quat_mul, external/rtm/includes/rtm/quatf.h:498-545 (SSE2 path: the signs are xor-ed into the products)
+		__device__ __forceinline__ Quat quat_mul(const Quat& l, const Quat& r)
+		{
+			Quat out;
+			out.x = add(add(mul(r.w, l.x), mul(r.x, l.w)), add(mul(r.y, l.z), -mul(r.z, l.y)));
+			out.y = add(add(mul(r.w, l.y), -mul(r.x, l.z)), add(mul(r.y, l.w), mul(r.z, l.x)));
+			out.z = add(add(mul(r.w, l.z), mul(r.x, l.y)), add(-mul(r.y, l.x), mul(r.z, l.w)));
+			out.w = add(add(mul(r.w, l.w), -mul(r.x, l.x)), add(-mul(r.y, l.y), -mul(r.z, l.z)));
+			return out;
+		}
+
+		// rtm::quat_mul_vector3, quatf.h:616-668 (SSE2 path): temp = conjugate(r) * (v, 0) without its W terms, result = temp * r
+		__device__ __forceinline__ Vec3 quat_mul_vector3(const Vec3& v, const Quat& r)
+		{
+			const float nx = -r.x, ny = -r.y, nz = -r.z;
+			const float t0 = add(add(mul(v.x, r.w), mul(v.y, nz)), mul(v.z, r.y));
+			const float t1 = add(add(mul(v.x, r.z), mul(v.y, r.w)), mul(v.z, nx));
+			const float t2 = add(add(mul(v.x, ny), mul(v.y, r.x)), mul(v.z, r.w));
+			const float t3 = add(add(mul(v.x, r.x), mul(v.y, r.y)), mul(v.z, r.z));
+			Vec3 out;
+			out.x = add(add(mul(r.w, t0), mul(r.x, t3)), add(mul(r.y, t2), mul(nz, t1)));
+			out.y = add(add(mul(r.w, t1), mul(nx, t2)), add(mul(r.y, t3), mul(r.z, t0)));
+			out.z = add(add(mul(r.w, t2), mul(r.x, t1)), add(mul(ny, t0), mul(r.z, t3)));
+			return out;
+		}
+
+		// rtm::quat_normalize, quatf.h:917-953: dot = (x2 + z2) + (y2 + w2); IEEE 1 / sqrt in place of the rsqrtss + 2 Newton-Raphson steps
+		__device__ __forceinline__ Quat quat_normalize(const Quat& q)
+		{
+			const float dot = add(add(mul(q.x, q.x), mul(q.z, q.z)), add(mul(q.y, q.y), mul(q.w, q.w)));
+			const float inv_len = __fdiv_rn(1.0f, __fsqrt_rn(dot));
+			Quat out;
+			out.x = mul(q.x, inv_len);
+			out.y = mul(q.y, inv_len);
+			out.z = mul(q.z, inv_len);
+			out.w = mul(q.w, inv_len);
+			return out;
+		}
+
+		// rtm::qvv_normalize(rtm::qvv_mul(local, parent_object)), external/rtm/includes/rtm/qvvf.h:315-355,426-430, positive scale branch.
+		// `negative` reports the case the reference sends through matrices (any min(lhs.scale, rhs.scale) component < 0).
+		__device__ __forceinline__ Qvv qvv_mul_normalize(const Qvv& local, const Qvv& parent, bool& negative)
+		{
+			negative = fminf(local.scale.x, parent.scale.x) < 0.0f || fminf(local.scale.y, parent.scale.y) < 0.0f || fminf(local.scale.z, parent.scale.z) < 0.0f;
+			Qvv out;
+			out.rotation = quat_normalize(quat_mul(local.rotation, parent.rotation));
+			Vec3 scaled;
+			scaled.x = mul(local.translation.x, parent.scale.x);
+			scaled.y = mul(local.translation.y, parent.scale.y);
+			scaled.z = mul(local.translation.z, parent.scale.z);
+			const Vec3 rotated = quat_mul_vector3(scaled, parent.rotation);
+			out.translation.x = add(rotated.x, parent.translation.x);
+			out.translation.y = add(rotated.y, parent.translation.y);
+			out.translation.z = add(rotated.z, parent.translation.z);
+			out.scale.x = mul(local.scale.x, parent.scale.x);
+			out.scale.y = mul(local.scale.y, parent.scale.y);
+			out.scale.z = mul(local.scale.z, parent.scale.z);
+			return out;
+		}
+
+		// rtm::qvv_mul_point3, qvvf.h:370-373
+		__device__ __forceinline__ Vec3 qvv_mul_point3(const Vec3& point, const Qvv& qvv)
+		{
+			Vec3 scaled;
+			scaled.x = mul(qvv.scale.x, point.x);
+			scaled.y = mul(qvv.scale.y, point.y);
+			scaled.z = mul(qvv.scale.z, point.z);
+			const Vec3 rotated = quat_mul_vector3(scaled, qvv.rotation);
+			Vec3 out;
+			out.x = add(rotated.x, qvv.translation.x);
+			out.y = add(rotated.y, qvv.translation.y);
+			out.z = add(rotated.z, qvv.translation.z);
+			return out;
+		}
+
+		// rtm::vector_distance3_as_scalar, vector4f.h:2260-2264 (dot3 = (x2 + y2) + z2, :1899-1906; sqrtss)
+		__device__ __forceinline__ float distance3(const Vec3& a, const Vec3& b)
+		{
+			const float dx = sub(a.x, b.x), dy = sub(a.y, b.y), dz = sub(a.z, b.z);
+			return __fsqrt_rn(add(add(mul(dx, dx), mul(dy, dy)), mul(dz, dz)));
+		}
+
+		__device__ __forceinline__ float max_ss(float a, float b) { return a > b ? a : b; }		// _mm_max_ss: the second operand when unordered
+
+		// qvvf_transform_error_metric::calculate_error, transform_error_metrics.h:335-358 (shell points of construct_sphere_shell :261-266)
+		__device__ __forceinline__ float calculate_error(const Qvv& raw, const Qvv& lossy, float shell_distance)
+		{
+			float error = 0.0f;
+			#pragma unroll
+			for (int axis = 0; axis < 3; ++axis)
+			{
+				Vec3 point;
+				point.x = axis == 0 ? shell_distance : 0.0f;
+				point.y = axis == 1 ? shell_distance : 0.0f;
+				point.z = axis == 2 ? shell_distance : 0.0f;
+				const float axis_error = distance3(qvv_mul_point3(point, raw), qvv_mul_point3(point, lossy));
+				error = axis == 0 ? axis_error : max_ss(error, axis_error);
+			}
+			return error;
+		}
+
+		__device__ __forceinline__ Qvv load_qvv48(const uint8_t* bone)
+		{
+			const float4 r = __ldg(reinterpret_cast<const float4*>(bone));
+			const float4 t = __ldg(reinterpret_cast<const float4*>(bone + 16));
+			const float4 s = __ldg(reinterpret_cast<const float4*>(bone + 32));
+			Qvv out;
+			out.rotation = Quat{ r.x, r.y, r.z, r.w };
+			out.translation = Vec3{ t.x, t.y, t.z };
+			out.scale = Vec3{ s.x, s.y, s.z };
+			return out;
+		}
+
+		__device__ __forceinline__ void store_planes(float* planes, uint32_t plane_stride, uint32_t bone, const Qvv& q)
+		{
+			planes[0 * plane_stride + bone] = q.rotation.x;
+			planes[1 * plane_stride + bone] = q.rotation.y;
+			planes[2 * plane_stride + bone] = q.rotation.z;
+			planes[3 * plane_stride + bone] = q.rotation.w;
+			planes[4 * plane_stride + bone] = q.translation.x;
+			planes[5 * plane_stride + bone] = q.translation.y;
+			planes[6 * plane_stride + bone] = q.translation.z;
+			planes[7 * plane_stride + bone] = q.scale.x;
+			planes[8 * plane_stride + bone] = q.scale.y;
+			planes[9 * plane_stride + bone] = q.scale.z;
+		}
+
+		__device__ __forceinline__ Qvv load_planes(const float* planes, uint32_t plane_stride, uint32_t bone)
+		{
+			Qvv q;
+			q.rotation.x = planes[0 * plane_stride + bone];
+			q.rotation.y = planes[1 * plane_stride + bone];
+			q.rotation.z = planes[2 * plane_stride + bone];
+			q.rotation.w = planes[3 * plane_stride + bone];
+			q.translation.x = planes[4 * plane_stride + bone];
+			q.translation.y = planes[5 * plane_stride + bone];
+			q.translation.z = planes[6 * plane_stride + bone];
+			q.scale.x = planes[7 * plane_stride + bone];
+			q.scale.y = planes[8 * plane_stride + bone];
+			q.scale.z = planes[9 * plane_stride + bone];
+			return q;
+		}
+
+		// arg max key: larger error wins, then the EARLIER (sample, bone) -- the reference keeps the first maximum it meets walking samples
+		// then bones with a strict `>` (track_error.impl.h:367-372). Errors are >= +0 or NaN (never kept), so their bit patterns order like
+		// the values. 0 = nothing measured yet.
+		__device__ __forceinline__ unsigned long long error_key(float error, uint32_t linear_index)
+		{
+			return ((static_cast<unsigned long long>(__float_as_uint(error)) + 1ull) << 32) | static_cast<unsigned long long>(~linear_index);
+		}
+
+		// sample_time = rtm::scalar_min(float(sample_index) / sample_rate, duration), track_error.impl.h:337 / :189
+		__device__ __forceinline__ float error_sample_time(uint32_t sample, float sample_rate, float duration)
+		{
+			const float t = __fdiv_rn(static_cast<float>(sample), sample_rate);
+			return t < duration ? t : duration;
+		}
+
+		// One thread per pose of the chunk: which job it belongs to, and the (clip, sample_time) request the decode kernels take.
+		__global__ void build_error_requests_kernel(ErrorParams p)
+		{
+			const uint32_t pose = blockIdx.x * blockDim.x + threadIdx.x;
+			if (pose >= p.num_poses)
+				return;
+			uint32_t lo = 0, hi = p.num_jobs;			// last job whose first pose is <= pose (jobs without samples share a first pose: skipped)
+			while (hi - lo > 1)
+			{
+				const uint32_t mid = (lo + hi) >> 1;
+				if (p.jobs[mid].chunk_first_pose <= pose)
+					lo = mid;
+				else
+					hi = mid;
+			}
+			const ErrorJobDev job = p.jobs[lo];
+			aclb200_request request;
+			request.clip = job.clip;
+			request.sample_time = error_sample_time(pose - job.chunk_first_pose, job.sample_rate, job.duration);
+			p.requests[pose] = request;
+			p.pose_jobs[pose] = lo;
+		}
+
+		// MODE 0: error measurement (two pose streams: raw + lossy), MODE 1: local_to_object_space of one stream, object poses written out.
+		struct ObjectSpaceParams
+		{
+			const uint8_t* local_poses;
+			uint8_t* object_poses;
+			uint64_t num_poses;
+			uint64_t pose_stride;
+			uint32_t num_tracks;
+			const uint32_t* parent_indices;
+			uint32_t plane_stride;
+			uint32_t* flags;				// [1]
+		};
+
+		template<int MODE>
+		__global__ void __launch_bounds__(256) object_space_kernel(ErrorParams ep, ObjectSpaceParams op)
+		{
+			extern __shared__ float object_planes[];
+			const uint32_t lane = threadIdx.x & 31u;
+			const uint32_t warp = threadIdx.x >> 5;
+			const uint32_t warps_per_block = blockDim.x >> 5;
+			const uint32_t plane_stride = MODE == 0 ? ep.plane_stride : op.plane_stride;
+			constexpr uint32_t k_streams = MODE == 0 ? 2u : 1u;
+			float* raw_planes = object_planes + size_t(warp) * k_streams * k_object_components * plane_stride;
+			float* lossy_planes = raw_planes + k_object_components * plane_stride;
+			const uint64_t num_poses = MODE == 0 ? uint64_t(ep.num_poses) : op.num_poses;
+
+			for (uint64_t pose = uint64_t(blockIdx.x) * warps_per_block + warp; pose < num_poses; pose += uint64_t(gridDim.x) * warps_per_block)
+			{
+				uint32_t num_tracks, sample = 0, job_slot = 0;
+				const uint8_t* raw_pose;
+				const uint8_t* lossy_pose = nullptr;
+				const uint32_t* parents;
+				const float* shells = nullptr;
+				const uint32_t* output_indices = nullptr;
+				float* error_row = nullptr;
+				if (MODE == 0)
+				{
+					const ErrorJobDev job = ep.jobs[ep.pose_jobs[pose]];
+					num_tracks = job.num_tracks;
+					sample = uint32_t(pose) - job.chunk_first_pose;
+					job_slot = job.job_index;
+					raw_pose = ep.raw_poses + (job.first_raw_pose + sample) * ep.pose_stride;
+					lossy_pose = ep.lossy_poses + pose * ep.pose_stride;
+					parents = ep.parent_indices + job.skeleton_offset;
+					shells = ep.shell_distances + job.skeleton_offset;
+					output_indices = ep.output_indices != nullptr ? ep.output_indices + job.skeleton_offset : nullptr;
+					if (ep.error_matrix != nullptr)
+						error_row = ep.error_matrix + (job.out_pose_base + sample) * ep.error_stride;
+				}
+				else
+				{
+					num_tracks = op.num_tracks;
+					raw_pose = op.local_poses + pose * op.pose_stride;
+					parents = op.parent_indices;
+				}
+
+				float best_error = -1.0f;				// track_error.impl.h:333
+				uint32_t best_bone = k_invalid_track;
+				uint32_t pose_flags = 0;
+
+				for (uint32_t base = 0; base < num_tracks; base += 32)
+				{
+					const uint32_t bone = base + lane;
+					const bool active = bone < num_tracks;
+					uint32_t parent = k_invalid_track;
+					Qvv raw_local = {}, lossy_local = {};
+					float shell = 0.0f;
+					if (active)
+					{
+						parent = __ldg(parents + bone);
+						raw_local = load_qvv48(raw_pose + size_t(bone) * 48);
+						if (MODE == 0)
+						{
+							shell = __ldg(shells + bone);
+							// remap_output (track_error.impl.h:522-532): the raw value stands in for a bone the compressed clip does not output
+							const uint32_t output_index = output_indices != nullptr ? __ldg(output_indices + bone) : bone;
+							lossy_local = output_index != k_invalid_track ? load_qvv48(lossy_pose + size_t(output_index) * 48) : raw_local;
+						}
+						if (parent != k_invalid_track && parent >= bone)
+						{
+							// the reference would read an object transform it has not written yet: reported, the bone is treated as a root
+							pose_flags |= ACLB200_ERROR_FLAG_INVALID_SKELETON;
+							parent = k_invalid_track;
+						}
+					}
+
+					bool pending = active;
+					uint32_t done_mask = 0;				// bones of this chunk whose object transforms are in shared memory
+					while (__any_sync(0xFFFFFFFFu, pending))
+					{
+						const bool ready = pending && (parent == k_invalid_track || parent < base || ((done_mask >> (parent - base)) & 1u) != 0);
+						if (ready)
+						{
+							Qvv raw_object = raw_local, lossy_object = lossy_local;
+							if (parent != k_invalid_track)
+							{
+								bool negative_raw = false, negative_lossy = false;
+								raw_object = qvv_mul_normalize(raw_local, load_planes(raw_planes, plane_stride, parent), negative_raw);
+								if (MODE == 0)
+									lossy_object = qvv_mul_normalize(lossy_local, load_planes(lossy_planes, plane_stride, parent), negative_lossy);
+								if (negative_raw || negative_lossy)
+									pose_flags |= ACLB200_ERROR_FLAG_NEGATIVE_SCALE;
+							}
+							store_planes(raw_planes, plane_stride, bone, raw_object);
+							if (MODE == 0)
+							{
+								store_planes(lossy_planes, plane_stride, bone, lossy_object);
+								const float error = calculate_error(raw_object, lossy_object, shell);
+								if (error_row != nullptr)
+									error_row[bone] = error;
+								if (error > best_error)
+								{
+									best_error = error;
+									best_bone = bone;
+								}
+							}
+							else
+							{
+								float4* out = reinterpret_cast<float4*>(op.object_poses + pose * op.pose_stride + size_t(bone) * 48);
+								out[0] = make_float4(raw_object.rotation.x, raw_object.rotation.y, raw_object.rotation.z, raw_object.rotation.w);
+								out[1] = make_float4(raw_object.translation.x, raw_object.translation.y, raw_object.translation.z, 0.0f);
+								out[2] = make_float4(raw_object.scale.x, raw_object.scale.y, raw_object.scale.z, 0.0f);
+							}
+							pending = false;
+						}
+						__syncwarp();
+						done_mask |= __ballot_sync(0xFFFFFFFFu, ready);
+					}
+				}
+				__syncwarp();		// the next pose overwrites the planes
+
+				if (MODE == 0)
+				{
+					// first maximum of the pose: larger error, then the smaller bone index (a lane's own bones already come in rising order)
+					#pragma unroll
+					for (int offset = 16; offset > 0; offset >>= 1)
+					{
+						const float other_error = __shfl_xor_sync(0xFFFFFFFFu, best_error, offset);
+						const uint32_t other_bone = __shfl_xor_sync(0xFFFFFFFFu, best_bone, offset);
+						if (other_error > best_error || (other_error == best_error && other_bone < best_bone))
+						{
+							best_error = other_error;
+							best_bone = other_bone;
+						}
+					}
+					pose_flags = __reduce_or_sync(0xFFFFFFFFu, pose_flags);
+					if (lane == 0)
+					{
+						if (best_bone != k_invalid_track)
+							atomicMax(ep.keys + job_slot, error_key(best_error, sample * num_tracks + best_bone));
+						if (pose_flags != 0)
+							atomicOr(ep.flags + job_slot, pose_flags);
+					}
+				}
+				else
+				{
+					pose_flags = __reduce_or_sync(0xFFFFFFFFu, pose_flags);
+					if (lane == 0 && pose_flags != 0 && op.flags != nullptr)
+						atomicOr(op.flags, pose_flags);
+				}
+			}
+		}
+
+		// calculate_scalar_track_error (track_error.impl.h:166-223) + get_scalar_track_error (:51-101): one thread per (pose, track)
+		__global__ void scalar_error_kernel(ErrorParams p, uint32_t max_tracks)
+		{
+			const uint64_t item = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+			const uint64_t pose = item / max_tracks;
+			const uint32_t track = uint32_t(item % max_tracks);
+			if (pose >= p.num_poses)
+				return;
+			const ErrorJobDev job = p.jobs[p.pose_jobs[pose]];
+			if (track >= job.num_tracks)
+				return;
+			const uint32_t sample = uint32_t(pose) - job.chunk_first_pose;
+			const float* raw = reinterpret_cast<const float*>(p.raw_poses + (job.first_raw_pose + sample) * p.pose_stride) + size_t(track) * p.components;
+			const float* lossy = reinterpret_cast<const float*>(p.lossy_poses + pose * p.pose_stride) + size_t(track) * p.components;
+			float e[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+			for (uint32_t c = 0; c < p.components; ++c)
+				e[c] = fabsf(sub(__ldg(raw + c), __ldg(lossy + c)));
+			// vector_get_max_component (external/rtm/includes/rtm/impl/vector_common.h:508-523): max(max(x, z), max(y, w)); float1f broadcasts x
+			const float error = p.components == 1 ? e[0] : max_ss(max_ss(e[0], e[2]), max_ss(e[1], e[3]));
+			if (p.error_matrix != nullptr)
+				p.error_matrix[(job.out_pose_base + sample) * p.error_stride + track] = error;
+			if (error >= 0.0f)			// never a NaN: `error > result.error` is false for it
+				atomicMax(p.keys + job.job_index, error_key(error, sample * job.num_tracks + track));
+		}
+
+		// One thread per job: the arg max key back into acl::track_error
+		__global__ void finalize_error_kernel(const ErrorJobDev* jobs, uint32_t num_jobs, const unsigned long long* keys, const uint32_t* flags, aclb200_track_error* out)
+		{
+			const uint32_t index = blockIdx.x * blockDim.x + threadIdx.x;
+			if (index >= num_jobs)
+				return;
+			const ErrorJobDev job = jobs[index];
+			aclb200_track_error result;
+			result.index = k_invalid_track;			// track_error(), compression/track_error.h:48-62
+			result.error = 0.0f;
+			result.sample_time = 0.0f;
+			result.flags = flags[job.job_index];
+			if (job.num_samples != 0 && job.num_tracks != 0)
+			{
+				const unsigned long long key = keys[job.job_index];
+				if (key == 0)
+					result.error = -1.0f;				// nothing compared greater than -1: every error was a NaN
+				else
+				{
+					const uint32_t linear = ~uint32_t(key & 0xFFFFFFFFull);
+					const uint32_t sample = linear / job.num_tracks;
+					result.index = linear - sample * job.num_tracks;
+					result.error = __uint_as_float(uint32_t(key >> 32) - 1u);
+					result.sample_time = error_sample_time(sample, job.sample_rate, job.duration);
+				}
+			}
+			out[job.job_index] = result;
+		}
+
+		uint32_t plane_stride_for(uint32_t num_tracks)
+		{
+			return (std::max(num_tracks, 1u) + 31u) & ~31u;
+		}
+
+		// warps per block so that the object transform planes fit; 0 = the skeleton is too wide for shared memory
+		uint32_t warps_for(uint32_t plane_stride, uint32_t streams, int max_dynamic_smem)
+		{
+			const size_t per_warp = size_t(streams) * k_object_components * plane_stride * sizeof(float);
+			const size_t budget = max_dynamic_smem > 0 ? size_t(max_dynamic_smem) : 0;
+			if (per_warp > budget)
+				return 0;
+			// two blocks per SM when they fit (the wavefront loop leaves lanes idle: more warps hide it)
+			const size_t block_budget = std::max(per_warp, std::min(budget, size_t(100) * 1024));
+			return uint32_t(std::min<size_t>(8, block_budget / per_warp));
+		}
+
+		aclb200_status grow_scratch(aclb200_context* context, size_t bytes)
+		{
+			if (context->error_scratch_bytes >= bytes)
+				return ACLB200_OK;
+			cudaFree(context->d_error_scratch);
+			context->d_error_scratch = nullptr;
+			context->error_scratch_bytes = 0;
+			const cudaError_t error = cudaMalloc(&context->d_error_scratch, bytes);
+			if (error != cudaSuccess)
+				return check_cuda(context, error, "calculate_compression_error: scratch allocation");
+			context->error_scratch_bytes = bytes;
+			return ACLB200_OK;
+		}
+
+		size_t align_up(size_t value, size_t alignment) { return (value + alignment - 1) / alignment * alignment; }
+	}
+
+	cudaError_t configure_error_kernels(int optin_limit)
+	{
+		cudaError_t error = cudaFuncSetAttribute(object_space_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin_limit);
+		if (error == cudaSuccess)
+			error = cudaFuncSetAttribute(object_space_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin_limit);
+		return error;
+	}
+}
+
+using namespace aclb200;
+
+extern "C"
+{
+	aclb200_status aclb200_local_to_object_space(aclb200_context* context, const void* d_local_poses, void* d_object_poses, uint64_t num_poses,
+		uint32_t num_tracks, uint64_t pose_stride_bytes, const uint32_t* d_parent_indices, uint32_t* d_out_flags, void* stream)
+	{
+		if (context == nullptr)
+			return ACLB200_ERR_INVALID_ARGUMENT;
+		if (num_poses == 0 || num_tracks == 0)
+			return ACLB200_OK;
+		if (d_local_poses == nullptr || d_object_poses == nullptr || d_parent_indices == nullptr)
+			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "local_to_object_space: null pose / parent pointer");
+		const uint64_t stride = pose_stride_bytes != 0 ? pose_stride_bytes : uint64_t(num_tracks) * 48;
+		if (stride < uint64_t(num_tracks) * 48 || (stride % 16) != 0 || (reinterpret_cast<uintptr_t>(d_local_poses) % 16) != 0 || (reinterpret_cast<uintptr_t>(d_object_poses) % 16) != 0)
+			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "local_to_object_space: poses are rtm::qvvf rows (48 byte bones), 16 byte aligned");
+
+		ObjectSpaceParams op = {};
+		op.local_poses = static_cast<const uint8_t*>(d_local_poses);
+		op.object_poses = static_cast<uint8_t*>(d_object_poses);
+		op.num_poses = num_poses;
+		op.pose_stride = stride;
+		op.num_tracks = num_tracks;
+		op.parent_indices = d_parent_indices;
+		op.plane_stride = plane_stride_for(num_tracks);
+		op.flags = d_out_flags;
+		const uint32_t warps = warps_for(op.plane_stride, 1, context->max_dynamic_smem);
+		if (warps == 0)
+			return set_error(context, ACLB200_ERR_UNSUPPORTED, "local_to_object_space: the skeleton's object transforms do not fit in shared memory");
+
+		cudaSetDevice(context->device);
+		cudaStream_t cuda_stream = static_cast<cudaStream_t>(stream);
+		if (d_out_flags != nullptr)
+		{
+			const cudaError_t cleared = cudaMemsetAsync(d_out_flags, 0, sizeof(uint32_t), cuda_stream);
+			if (cleared != cudaSuccess)
+				return check_cuda(context, cleared, "local_to_object_space");
+		}
+		const uint64_t blocks_needed = (num_poses + warps - 1) / warps;
+		const uint32_t blocks = uint32_t(std::min<uint64_t>(blocks_needed, uint64_t(context->num_sms) * 32));
+		const size_t smem = size_t(warps) * k_object_components * op.plane_stride * sizeof(float);
+		object_space_kernel<1><<<blocks, warps * 32, smem, cuda_stream>>>(ErrorParams{}, op);
+		const cudaError_t error = cudaGetLastError();
+		if (error == cudaSuccess)
+			context->launch_count++;
+		return check_cuda(context, error, "local_to_object_space");
+	}
+
+	aclb200_status aclb200_calculate_compression_error(aclb200_context* context, const aclb200_clipset* clipset, const aclb200_error_job* jobs,
+		uint32_t num_jobs, const void* d_raw_poses, const uint32_t* d_parent_indices, const float* d_shell_distances,
+		const uint32_t* d_output_indices, const aclb200_options* options, aclb200_track_error* d_out_errors, float* d_out_error_matrix, void* stream)
+	{
+		if (context == nullptr || clipset == nullptr || options == nullptr)
+			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "null context / clipset / options");
+		if (options->struct_size != sizeof(aclb200_options))
+			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "options.struct_size does not match this library, call aclb200_default_options()");
+		if (num_jobs == 0)
+			return ACLB200_OK;
+		if (jobs == nullptr || d_raw_poses == nullptr || d_out_errors == nullptr)
+			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "calculate_compression_error: null jobs / raw poses / output");
+		const bool is_transform = clipset->info.track_type == ACLB200_TRACK_QVVF;
+		if (is_transform && (d_parent_indices == nullptr || d_shell_distances == nullptr))
+			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "calculate_compression_error: transform clips need parent indices and shell distances");
+		// The reference measures with a debug_track_writer that skips default sub-tracks over a buffer holding the bind pose
+		// (track_error.impl.h:497-501, debug_track_writer.h:75-101): here the bind pose arrives as constant / variable defaults.
+		if (is_transform && (options->default_rotation_mode == ACLB200_DEFAULT_SKIPPED || options->default_translation_mode == ACLB200_DEFAULT_SKIPPED
+			|| options->default_scale_mode == ACLB200_DEFAULT_SKIPPED || (options->skip_mask & 7u) != 0 || options->d_skip_track_mask != nullptr))
+			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "calculate_compression_error: skipped sub-tracks have no value to measure, pass the bind pose as constant / variable defaults");
+		if (options->rounding_policy == ACLB200_ROUND_PER_TRACK || options->d_request_policies != nullptr)
+			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "calculate_compression_error picks the rounding policy itself (nearest, none for stripped clips)");
+
+		const uint32_t components = is_transform ? 0u : (clipset->info.track_type <= 3 ? clipset->info.track_type + 1 : 4u);
+		const uint32_t bone_stride = is_transform ? 48u : components * 4u;
+		const uint64_t stride = options->pose_stride_bytes != 0 ? options->pose_stride_bytes : uint64_t(clipset->info.max_tracks) * bone_stride;
+		const uint64_t alignment = is_transform ? 16 : 4;
+		if ((stride % alignment) != 0 || (reinterpret_cast<uintptr_t>(d_raw_poses) % alignment) != 0)
+			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "calculate_compression_error: raw poses must be 16 byte aligned rtm::qvvf rows (4 byte aligned scalar rows)");
+
+		// jobs in processing order: the clips sought with `nearest`, then the ones sought with `none` (stripped key frames leave holes
+		// nearest would land in, track_error.impl.h:556-559); each group is decoded by launches of its own
+		std::vector<ErrorJobDev> ordered;
+		ordered.reserve(num_jobs);
+		std::vector<uint64_t> out_base(num_jobs);
+		uint64_t total_poses = 0;
+		uint32_t widest = 0;
+		for (uint32_t index = 0; index < num_jobs; ++index)
+		{
+			const aclb200_error_job& job = jobs[index];
+			if (job.clip >= clipset->info.num_clips)
+				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "calculate_compression_error: job names a clip outside the clip set");
+			if (uint64_t(job.num_tracks) * bone_stride > stride)
+				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "calculate_compression_error: job has more tracks than a pose row holds");
+			if (d_output_indices == nullptr && job.num_tracks != clipset->host_clips[job.clip].num_tracks)
+				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "calculate_compression_error: raw and compressed track counts differ (pass output indices)");
+			if (uint64_t(job.num_samples) * std::max(job.num_tracks, 1u) > 0xFFFFFFFFull)
+				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "calculate_compression_error: samples x tracks of a job must fit 32 bits");
+			out_base[index] = total_poses;
+			total_poses += job.num_samples;
+			widest = std::max(widest, job.num_tracks);
+		}
+		size_t group_begin[3] = { 0, 0, 0 };
+		for (uint32_t pass = 0; pass < 2; ++pass)
+		{
+			for (uint32_t index = 0; index < num_jobs; ++index)
+			{
+				const aclb200_error_job& job = jobs[index];
+				const bool stripped = (clipset->host_clips[job.clip].flags & k_clip_stripped) != 0;
+				if (stripped != (pass == 1))
+					continue;
+				ErrorJobDev dev = {};
+				dev.clip = job.clip;
+				dev.num_samples = job.num_samples;
+				dev.num_tracks = job.num_tracks;
+				dev.skeleton_offset = job.skeleton_offset;
+				dev.sample_rate = job.sample_rate;
+				dev.duration = job.duration;
+				dev.job_index = index;
+				dev.first_raw_pose = job.first_raw_pose;
+				dev.out_pose_base = out_base[index];
+				ordered.push_back(dev);
+			}
+			group_begin[pass + 1] = ordered.size();
+		}
+
+		const uint32_t plane_stride = plane_stride_for(widest);
+		const uint32_t warps = is_transform ? warps_for(plane_stride, 2, context->max_dynamic_smem) : 8u;
+		if (warps == 0)
+			return set_error(context, ACLB200_ERR_UNSUPPORTED, "calculate_compression_error: the skeleton's object transforms do not fit in shared memory");
+
+		// chunks: runs of jobs of one group whose decoded poses fit the scratch budget (one job at least)
+		const uint64_t budget_poses = std::max<uint64_t>(1, context->error_chunk_bytes / std::max<uint64_t>(stride, 1));
+		struct Chunk { size_t first_job, num_jobs; uint32_t num_poses; uint32_t rounding; };
+		std::vector<Chunk> chunks;
+		uint64_t max_chunk_poses = 0;
+		for (uint32_t pass = 0; pass < 2; ++pass)
+		{
+			size_t cursor = group_begin[pass];
+			while (cursor < group_begin[pass + 1])
+			{
+				Chunk chunk = { cursor, 0, 0, pass == 0 ? uint32_t(ACLB200_ROUND_NEAREST) : uint32_t(ACLB200_ROUND_NONE) };
+				uint64_t poses = 0;
+				while (cursor < group_begin[pass + 1] && (chunk.num_jobs == 0 || poses + ordered[cursor].num_samples <= budget_poses))
+				{
+					ordered[cursor].chunk_first_pose = uint32_t(poses);
+					poses += ordered[cursor].num_samples;
+					++cursor;
+					++chunk.num_jobs;
+				}
+				if (poses > 0x7FFFFFFFull)
+					return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "calculate_compression_error: a single clip has too many samples");
+				chunk.num_poses = uint32_t(poses);
+				max_chunk_poses = std::max(max_chunk_poses, poses);
+				chunks.push_back(chunk);
+			}
+		}
+
+		// scratch carve-up: jobs | keys | flags | requests | pose jobs | lossy poses
+		const size_t jobs_bytes = align_up(sizeof(ErrorJobDev) * ordered.size(), 256);
+		const size_t keys_bytes = align_up(sizeof(unsigned long long) * num_jobs, 256);
+		const size_t flags_bytes = align_up(sizeof(uint32_t) * num_jobs, 256);
+		const size_t requests_bytes = align_up(sizeof(aclb200_request) * size_t(max_chunk_poses), 256);
+		const size_t pose_jobs_bytes = align_up(sizeof(uint32_t) * size_t(max_chunk_poses), 256);
+		const size_t lossy_bytes = align_up(size_t(max_chunk_poses) * size_t(stride), 256);
+		cudaSetDevice(context->device);
+		const aclb200_status grown = grow_scratch(context, jobs_bytes + keys_bytes + flags_bytes + requests_bytes + pose_jobs_bytes + lossy_bytes + 256);
+		if (grown != ACLB200_OK)
+			return grown;
+		uint8_t* scratch = static_cast<uint8_t*>(context->d_error_scratch);
+		ErrorJobDev* d_jobs = reinterpret_cast<ErrorJobDev*>(scratch);
+		unsigned long long* d_keys = reinterpret_cast<unsigned long long*>(scratch + jobs_bytes);
+		uint32_t* d_flags = reinterpret_cast<uint32_t*>(scratch + jobs_bytes + keys_bytes);
+		aclb200_request* d_requests = reinterpret_cast<aclb200_request*>(scratch + jobs_bytes + keys_bytes + flags_bytes);
+		uint32_t* d_pose_jobs = reinterpret_cast<uint32_t*>(scratch + jobs_bytes + keys_bytes + flags_bytes + requests_bytes);
+		uint8_t* d_lossy = scratch + jobs_bytes + keys_bytes + flags_bytes + requests_bytes + pose_jobs_bytes;
+
+		cudaStream_t cuda_stream = static_cast<cudaStream_t>(stream);
+		// pageable source: the copy has left `ordered` when the call returns
+		cudaError_t error = cudaMemcpyAsync(d_jobs, ordered.data(), sizeof(ErrorJobDev) * ordered.size(), cudaMemcpyHostToDevice, cuda_stream);
+		if (error == cudaSuccess)
+			error = cudaMemsetAsync(d_keys, 0, keys_bytes + flags_bytes, cuda_stream);
+		if (error != cudaSuccess)
+			return check_cuda(context, error, "calculate_compression_error: job upload");
+
+		aclb200_options decode_options = *options;
+		decode_options.output_layout = ACLB200_LAYOUT_QVV48;
+		decode_options.pose_stride_bytes = stride;
+		decode_options.d_request_policies = nullptr;
+
+		for (const Chunk& chunk : chunks)
+		{
+			if (chunk.num_poses == 0)
+				continue;
+			ErrorParams p = {};
+			p.jobs = d_jobs + chunk.first_job;
+			p.num_jobs = uint32_t(chunk.num_jobs);
+			p.num_poses = chunk.num_poses;
+			p.requests = d_requests;
+			p.pose_jobs = d_pose_jobs;
+			p.raw_poses = static_cast<const uint8_t*>(d_raw_poses);
+			p.lossy_poses = d_lossy;
+			p.pose_stride = stride;
+			p.parent_indices = d_parent_indices;
+			p.shell_distances = d_shell_distances;
+			p.output_indices = d_output_indices;
+			p.keys = d_keys;
+			p.flags = d_flags;
+			p.error_matrix = d_out_error_matrix;
+			p.error_stride = clipset->info.max_tracks;
+			p.plane_stride = plane_stride;
+			p.components = components;
+
+			build_error_requests_kernel<<<(chunk.num_poses + 255) / 256, 256, 0, cuda_stream>>>(p);
+			error = cudaGetLastError();
+			if (error != cudaSuccess)
+				return check_cuda(context, error, "calculate_compression_error: request setup");
+			context->launch_count++;
+
+			decode_options.rounding_policy = chunk.rounding;
+			const aclb200_status decoded = is_transform
+				? aclb200_decompress_tracks(context, clipset, d_requests, chunk.num_poses, &decode_options, d_lossy, stream)
+				: aclb200_scalar_decompress_tracks(context, clipset, d_requests, chunk.num_poses, &decode_options, d_lossy, stream);
+			if (decoded != ACLB200_OK)
+				return decoded;
+
+			if (is_transform)
+			{
+				const uint32_t blocks_needed = (chunk.num_poses + warps - 1) / warps;
+				const uint32_t blocks = std::min<uint32_t>(blocks_needed, uint32_t(context->num_sms) * 32);
+				const size_t smem = size_t(warps) * 2 * k_object_components * plane_stride * sizeof(float);
+				object_space_kernel<0><<<blocks, warps * 32, smem, cuda_stream>>>(p, ObjectSpaceParams{});
+			}
+			else
+			{
+				const uint64_t items = uint64_t(chunk.num_poses) * clipset->info.max_tracks;
+				scalar_error_kernel<<<uint32_t((items + 255) / 256), 256, 0, cuda_stream>>>(p, clipset->info.max_tracks);
+			}
+			error = cudaGetLastError();
+			if (error != cudaSuccess)
+				return check_cuda(context, error, "calculate_compression_error: error kernel");
+			context->launch_count++;
+		}
+
+		finalize_error_kernel<<<(num_jobs + 255) / 256, 256, 0, cuda_stream>>>(d_jobs, num_jobs, d_keys, d_flags, d_out_errors);
+		error = cudaGetLastError();
+		if (error == cudaSuccess)
+			context->launch_count++;
+		return check_cuda(context, error, "calculate_compression_error");
+	}
+
+	aclb200_status aclb200_set_error_chunk_bytes(aclb200_context* context, uint64_t bytes)
+	{
+		if (context == nullptr || bytes == 0)
+			return ACLB200_ERR_INVALID_ARGUMENT;
+		context->error_chunk_bytes = bytes;
+		return ACLB200_OK;
+	}
+}

@@ -758,6 +758,7 @@ namespace aclb200
 		if (error == cudaSuccess) error = set_smem_attribute<2, false>(optin_limit, available);
 		if (error == cudaSuccess) error = set_smem_attribute<2, true>(optin_limit, available);
 		if (error == cudaSuccess) error = configure_pipeline_kernels(optin_limit, available);
+		if (error == cudaSuccess) error = configure_error_kernels(available);
 		max_dynamic_smem = available;
 		return error;
 	}

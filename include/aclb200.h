@@ -234,6 +234,69 @@ ACLB200_API aclb200_status aclb200_scalar_decompress_track(aclb200_context* cont
 ACLB200_API aclb200_status aclb200_decompress_tracks_host(aclb200_context* context, const aclb200_clipset* clipset,
 	const aclb200_request* requests, uint32_t num_requests, const aclb200_options* options, void* out, size_t out_bytes);
 
+/* ---- the nearest callers of the decode path, on the device (acl_b200/csrc/error_metric.cu) ---------------- */
+
+/* acl::track_error (compression/track_error.h:48-62) + what this library could not follow the reference through */
+typedef struct aclb200_track_error
+{
+	uint32_t index;					/* track with the worst error (0xFFFFFFFF when nothing was measured) */
+	float    error;
+	float    sample_time;
+	uint32_t flags;					/* ACLB200_ERROR_FLAG_* */
+} aclb200_track_error;
+
+enum
+{
+	ACLB200_ERROR_FLAG_NEGATIVE_SCALE = 1,		/* a negative scale met rtm::qvv_mul's matrix branch (qvvf.h:320-345), which is not implemented: the
+												 * clip's numbers are NOT the reference's */
+	ACLB200_ERROR_FLAG_INVALID_SKELETON = 2		/* a parent index does not precede its child (the reference reads an unwritten transform there):
+												 * the bone was treated as a root */
+};
+
+/* One clip to measure == one `calculate_compression_error(allocator, raw_tracks, context, error_metric)` call of the reference
+ * (compression/track_error.h:64-121). The raw clip arrives already sampled: pose s of the job is what
+ * `raw_tracks.sample_tracks(min(s / sample_rate, duration), rounding, writer)` writes (track_error.impl.h:337-338,504-507), where rounding is
+ * nearest, or none when the compressed clip has stripped key frames (:556-559). */
+typedef struct aclb200_error_job
+{
+	uint32_t clip;					/* index into the clip set */
+	uint32_t num_samples;			/* raw_tracks.get_num_samples_per_track() */
+	float    sample_rate;			/* raw_tracks.get_sample_rate() */
+	float    duration;				/* raw_tracks.get_finite_duration() */
+	uint32_t num_tracks;			/* raw_tracks.get_num_tracks() */
+	uint32_t skeleton_offset;		/* first entry of this clip's skeleton in d_parent_indices / d_shell_distances / d_output_indices */
+	uint64_t first_raw_pose;		/* pose index of sample 0 in d_raw_poses */
+} aclb200_error_job;
+
+/* Replaces calculate_compression_error (compression/impl/track_error.impl.h:400-571: calculate_transform_track_error :225-392 with the
+ * qvvf_transform_error_metric of compression/transform_error_metrics.h:281-385, calculate_scalar_track_error :166-223) for `num_jobs` clips:
+ * every sample of every clip is decoded on the device (decompress_tracks, rounding as above, `options` = the settings / writer of the context
+ * the reference would be handed: pass the bind pose as constant or variable defaults), taken to object space and compared with the raw pose.
+ *   jobs              HOST array
+ *   d_raw_poses       device: pose p at p * pose_stride_bytes (options, 0 = max_tracks * 48): rtm::qvvf per bone (transform clip sets),
+ *                     `components` floats per track (scalar clip sets: the layout aclb200_scalar_decompress_tracks writes)
+ *   d_parent_indices  device: track_desc_transformf::parent_index per track (0xFFFFFFFF = root; a parent precedes its children),
+ *   d_shell_distances device: track_desc_transformf::shell_distance per track; both unused (NULL) for scalar clip sets
+ *   d_output_indices  device, optional: track_desc::output_index per raw track (0xFFFFFFFF = stripped from the compressed clip: the raw
+ *                     value stands in, track_error.impl.h:522-532); NULL = every raw track i is output i
+ *   d_out_errors      device: one aclb200_track_error per job
+ *   d_out_error_matrix device, optional: the error of every bone of every pose, row (poses of the earlier jobs + s) of max_tracks floats
+ * No additive base (track_error.impl.h:573-680). rtm::quat_normalize's rsqrtss estimate is CPU specific: errors agree with a given CPU's
+ * within 5e-5 on poses tens of units across, not bit for bit (see error_metric.cu). Asynchronous on `stream`; uses scratch owned by the context. */
+ACLB200_API aclb200_status aclb200_calculate_compression_error(aclb200_context* context, const aclb200_clipset* clipset, const aclb200_error_job* jobs,
+	uint32_t num_jobs, const void* d_raw_poses, const uint32_t* d_parent_indices, const float* d_shell_distances,
+	const uint32_t* d_output_indices, const aclb200_options* options, aclb200_track_error* d_out_errors, float* d_out_error_matrix, void* stream);
+
+/* Decoded poses held per chunk of clips by aclb200_calculate_compression_error (default 512 MiB). */
+ACLB200_API aclb200_status aclb200_set_error_chunk_bytes(aclb200_context* context, uint64_t bytes);
+
+/* Replaces qvvf_transform_error_metric::local_to_object_space (compression/transform_error_metrics.h:289-310: obj[i] =
+ * qvv_normalize(qvv_mul(local[i], obj[parent[i]])), roots copied) for `num_poses` poses of one skeleton: rtm::qvvf rows in, rtm::qvvf rows
+ * out (48 byte bones, pose_stride_bytes 0 = num_tracks * 48; the two buffers may be the same). d_out_flags (optional, device uint32):
+ * ACLB200_ERROR_FLAG_* met on the way. */
+ACLB200_API aclb200_status aclb200_local_to_object_space(aclb200_context* context, const void* d_local_poses, void* d_object_poses, uint64_t num_poses,
+	uint32_t num_tracks, uint64_t pose_stride_bytes, const uint32_t* d_parent_indices, uint32_t* d_out_flags, void* stream);
+
 /* Parity / debugging hooks (integer stages of the decode, bit-exact against the reference):
  *  - aclb200_debug_seek: the state seek_v0 computes, one aclb200_seek_state per request (device output).
  *  - aclb200_debug_unpack: for request r and key frame `which` (0/1), writes one uint4 per animated sub-track

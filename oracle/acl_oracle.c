@@ -1360,3 +1360,210 @@ double aclo_bench_transform(const void* const* blobs, const uint32_t* request_cl
 	clock_gettime(CLOCK_MONOTONIC, &t1);
 	return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * calculate_compression_error (compression/impl/track_error.impl.h:166-392) with the
+ * qvvf_transform_error_metric (compression/transform_error_metrics.h:281-385). rtm paths are relative to
+ * /root/reference/external/rtm/includes/rtm, SSE2 code paths (what oracle/_ref is compiled with).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* rtm::quat_mul, quatf.h:498-545 (SSE2): ((r.w*l + s0*(r.x*l_wzyx)) + (s1*(r.y*l_zwxy) + s2*(r.z*l_yxwz))), signs applied by xor */
+static void rtm_quat_mul(const float l[4], const float r[4], float out[4])
+{
+	const float a0 = r[3] * l[0], a1 = r[3] * l[1], a2 = r[3] * l[2], a3 = r[3] * l[3];
+	const float b0 = r[0] * l[3], b1 = -(r[0] * l[2]), b2 = r[0] * l[1], b3 = -(r[0] * l[0]);
+	const float c0 = r[1] * l[2], c1 = r[1] * l[3], c2 = -(r[1] * l[0]), c3 = -(r[1] * l[1]);
+	const float d0 = -(r[2] * l[1]), d1 = r[2] * l[0], d2 = r[2] * l[3], d3 = -(r[2] * l[2]);
+	out[0] = (a0 + b0) + (c0 + d0);
+	out[1] = (a1 + b1) + (c1 + d1);
+	out[2] = (a2 + b2) + (c2 + d2);
+	out[3] = (a3 + b3) + (c3 + d3);
+}
+
+/* rtm::quat_mul_vector3, quatf.h:616-668 (SSE2): temp = conj(r) * (v, 0) without the W terms, result = temp * r */
+static void rtm_quat_mul_vector3(const float v[3], const float r[4], float out[3])
+{
+	const float nx = -r[0], ny = -r[1], nz = -r[2];
+	const float t0 = (v[0] * r[3] + v[1] * nz) + v[2] * r[1];
+	const float t1 = (v[0] * r[2] + v[1] * r[3]) + v[2] * nx;
+	const float t2 = (v[0] * ny + v[1] * r[0]) + v[2] * r[3];
+	const float t3 = (v[0] * r[0] + v[1] * r[1]) + v[2] * r[2];
+	out[0] = (r[3] * t0 + r[0] * t3) + (r[1] * t2 + nz * t1);
+	out[1] = (r[3] * t1 + nx * t2) + (r[1] * t3 + r[2] * t0);
+	out[2] = (r[3] * t2 + r[0] * t1) + (ny * t0 + r[2] * t3);
+}
+
+/* rtm::quat_normalize, quatf.h:917-953. mode 0: the SSE2 code (rsqrtss estimate + 2 Newton-Raphson steps; the estimate is CPU specific,
+ * so this is bit-identical to the reference only on the CPU both run on); mode 1: IEEE 1 / sqrt (what the CUDA path computes). */
+static void metric_quat_normalize(float q[4], int normalize_mode)
+{
+	if (normalize_mode == 0)
+	{
+		rtm_quat_normalize(q);
+		return;
+	}
+	const float x2 = q[0] * q[0], y2 = q[1] * q[1], z2 = q[2] * q[2], w2 = q[3] * q[3];
+	const float dot = (x2 + z2) + (y2 + w2);
+	const float inv_len = 1.0f / sqrtf(dot);
+	for (int i = 0; i < 4; ++i)
+		q[i] = q[i] * inv_len;
+}
+
+/* rtm::qvv_normalize(rtm::qvv_mul(local, parent_object)), qvvf.h:315-355,426-430: the positive scale branch. Returns 1 when the
+ * reference would take the negative scale branch (through matrices), which this port does not restate. */
+static int qvv_mul_normalize(const float local[12], const float parent[12], int normalize_mode, float out[12])
+{
+	int negative = 0;
+	for (int i = 0; i < 3; ++i)
+	{
+		const float min_scale = local[8 + i] < parent[8 + i] ? local[8 + i] : parent[8 + i];	/* _mm_min_ps(lhs, rhs) */
+		negative |= min_scale < 0.0f;
+	}
+	float rotation[4];
+	rtm_quat_mul(local + 0, parent + 0, rotation);
+	const float scaled[3] = { local[4] * parent[8], local[5] * parent[9], local[6] * parent[10] };
+	float rotated[3];
+	rtm_quat_mul_vector3(scaled, parent + 0, rotated);
+	metric_quat_normalize(rotation, normalize_mode);
+	for (int i = 0; i < 4; ++i)
+		out[i] = rotation[i];
+	for (int i = 0; i < 3; ++i)
+	{
+		out[4 + i] = rotated[i] + parent[4 + i];
+		out[8 + i] = local[8 + i] * parent[8 + i];
+	}
+	out[7] = 0.0f;
+	out[11] = 0.0f;
+	return negative;
+}
+
+/* qvvf_transform_error_metric::local_to_object_space, transform_error_metrics.h:289-310 (all transforms dirty, in index order) */
+int aclo_local_to_object_space(const float* local_pose, const uint32_t* parent_indices, uint32_t num_tracks, int normalize_mode, float* out_object_pose)
+{
+	int negative = 0;
+	for (uint32_t bone = 0; bone < num_tracks; ++bone)
+	{
+		const uint32_t parent = parent_indices[bone];
+		if (parent == 0xFFFFFFFFu)
+			memcpy(out_object_pose + (size_t)bone * 12, local_pose + (size_t)bone * 12, 12 * sizeof(float));
+		else if (parent >= bone)
+			return -1;		/* the reference reads a stale / unwritten parent here: not a valid skeleton order */
+		else
+			negative |= qvv_mul_normalize(local_pose + (size_t)bone * 12, out_object_pose + (size_t)parent * 12, normalize_mode, out_object_pose + (size_t)bone * 12);
+	}
+	return negative;
+}
+
+/* rtm::qvv_mul_point3, qvvf.h:370-373 */
+static void qvv_mul_point3(const float point[3], const float qvv[12], float out[3])
+{
+	const float scaled[3] = { qvv[8] * point[0], qvv[9] * point[1], qvv[10] * point[2] };
+	float rotated[3];
+	rtm_quat_mul_vector3(scaled, qvv, rotated);
+	for (int i = 0; i < 3; ++i)
+		out[i] = rotated[i] + qvv[4 + i];
+}
+
+/* rtm::vector_distance3_as_scalar, vector4f.h:2260-2264 -> vector_dot3_as_scalar :1899-1906 (SSE2: (x2 + y2) + z2), scalar_sqrt = sqrtss */
+static float vector_distance3(const float a[3], const float b[3])
+{
+	const float dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+	return sqrtf((dx * dx + dy * dy) + dz * dz);
+}
+
+static float sse_max_ss(float a, float b) { return a > b ? a : b; }		/* _mm_max_ss(a, b): b when unordered */
+
+/* qvvf_transform_error_metric::calculate_error, transform_error_metrics.h:335-358 with construct_sphere_shell :261-266 */
+float aclo_calculate_error(const float* raw_object_bone, const float* lossy_object_bone, float shell_distance)
+{
+	float errors[3];
+	for (int axis = 0; axis < 3; ++axis)
+	{
+		float point[3] = { 0.0f, 0.0f, 0.0f };
+		point[axis] = shell_distance;
+		float raw_vtx[3], lossy_vtx[3];
+		qvv_mul_point3(point, raw_object_bone, raw_vtx);
+		qvv_mul_point3(point, lossy_object_bone, lossy_vtx);
+		errors[axis] = vector_distance3(raw_vtx, lossy_vtx);
+	}
+	return sse_max_ss(sse_max_ss(errors[0], errors[1]), errors[2]);
+}
+
+/* The sample loop of calculate_transform_track_error (track_error.impl.h:225-392) once both pose streams are sampled:
+ * raw_poses = raw_tracks.sample_tracks(t_i), lossy_poses = seek(t_i) + decompress_tracks (already remapped, :341), both
+ * [num_samples][num_tracks][12]; t_i = min(i / sample_rate, duration) (:337). No additive base. out_errors (optional):
+ * [num_samples][num_tracks]. Returns < 0 for an invalid skeleton order, 1 if a negative scale was met (result not the reference's). */
+int aclo_transform_track_error(const float* raw_poses, const float* lossy_poses, uint32_t num_samples, uint32_t num_tracks,
+	float sample_rate, float duration, const uint32_t* parent_indices, const float* shell_distances, int normalize_mode,
+	aclo_track_error* out_error, float* out_errors, float* scratch_object_poses /* [2][num_tracks][12] */)
+{
+	out_error->index = 0xFFFFFFFFu;		/* track_error(), track_error.h:48-62 */
+	out_error->error = 0.0f;
+	out_error->sample_time = 0.0f;
+	if (num_samples == 0 || num_tracks == 0)
+		return 0;						/* :229-235 */
+	out_error->error = -1.0f;			/* :333 */
+
+	float* raw_object = scratch_object_poses;
+	float* lossy_object = scratch_object_poses + (size_t)num_tracks * 12;
+	int negative = 0;
+	for (uint32_t sample = 0; sample < num_samples; ++sample)
+	{
+		const float t = (float)sample / sample_rate;
+		const float sample_time = t < duration ? t : duration;		/* rtm::scalar_min */
+		const size_t pose = (size_t)sample * num_tracks * 12;
+		const int r0 = aclo_local_to_object_space(raw_poses + pose, parent_indices, num_tracks, normalize_mode, raw_object);
+		const int r1 = aclo_local_to_object_space(lossy_poses + pose, parent_indices, num_tracks, normalize_mode, lossy_object);
+		if (r0 < 0 || r1 < 0)
+			return -1;
+		negative |= r0 | r1;
+		for (uint32_t bone = 0; bone < num_tracks; ++bone)
+		{
+			const float error = aclo_calculate_error(raw_object + (size_t)bone * 12, lossy_object + (size_t)bone * 12, shell_distances[bone]);
+			if (out_errors != NULL)
+				out_errors[(size_t)sample * num_tracks + bone] = error;
+			if (error > out_error->error)		/* :367-372 */
+			{
+				out_error->error = error;
+				out_error->index = bone;
+				out_error->sample_time = sample_time;
+			}
+		}
+	}
+	return negative;
+}
+
+/* calculate_scalar_track_error, track_error.impl.h:166-223 with get_scalar_track_error :51-101: rows are [num_tracks][4] floats of which
+ * the first `components` are compared (float1f..float4f / vector4f). */
+int aclo_scalar_track_error(const float* raw_values, const float* lossy_values, uint32_t num_samples, uint32_t num_tracks, uint32_t components,
+	float sample_rate, float duration, aclo_track_error* out_error)
+{
+	out_error->index = 0xFFFFFFFFu;
+	out_error->error = 0.0f;
+	out_error->sample_time = 0.0f;
+	if (num_samples == 0 || num_tracks == 0)
+		return 0;
+	out_error->error = -1.0f;
+	for (uint32_t sample = 0; sample < num_samples; ++sample)
+	{
+		const float t = (float)sample / sample_rate;
+		const float sample_time = t < duration ? t : duration;
+		for (uint32_t track = 0; track < num_tracks; ++track)
+		{
+			const size_t row = ((size_t)sample * num_tracks + track) * 4;
+			/* abs(raw - lossy), unused lanes zeroed, vector_get_max_component = max(max(x, y), max(z, w)) (vector4f.h, SSE2 shuffles) */
+			float e[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+			for (uint32_t c = 0; c < components; ++c)
+				e[c] = fabsf(raw_values[row + c] - lossy_values[row + c]);
+			const float xz = sse_max_ss(e[0], e[2]), yw = sse_max_ss(e[1], e[3]);
+			const float max_error = components == 1 ? e[0] : sse_max_ss(xz, yw);
+			if (max_error > out_error->error)
+			{
+				out_error->error = max_error;
+				out_error->index = track;
+				out_error->sample_time = sample_time;
+			}
+		}
+	}
+	return 0;
+}

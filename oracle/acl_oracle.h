@@ -120,6 +120,27 @@ int aclo_scalar_decompress_track(const void* blob, const aclo_settings* settings
 int aclo_transform_touched_bytes(const void* blob, uint32_t segment_index, uint64_t out[4]);
 int aclo_scalar_touched_bytes(const void* blob, uint64_t out[4]);
 
+/* the reference's compression error measurement (compression/impl/track_error.impl.h:166-392) with the
+ * qvvf_transform_error_metric (compression/transform_error_metrics.h:281-385), restated over already sampled poses.
+ * normalize_mode 0 = rtm::quat_normalize as the reference's SSE2 build runs it (rsqrtss + 2 Newton-Raphson steps: bit-identical to
+ * the reference on the CPU both run on; tests pin it there), 1 = IEEE 1 / sqrt (what the CUDA path computes, bit for bit). */
+typedef struct aclo_track_error		/* acl::track_error, compression/track_error.h:48-62 */
+{
+	uint32_t index;
+	float    error;
+	float    sample_time;
+} aclo_track_error;
+
+/* poses are [num_tracks][12] floats (rtm::qvvf). Returns < 0 when a parent does not precede its child, 1 when a negative scale was met
+ * (the reference then goes through matrices, qvvf.h:320-345: not restated), else 0. */
+int aclo_local_to_object_space(const float* local_pose, const uint32_t* parent_indices, uint32_t num_tracks, int normalize_mode, float* out_object_pose);
+float aclo_calculate_error(const float* raw_object_bone, const float* lossy_object_bone, float shell_distance);
+int aclo_transform_track_error(const float* raw_poses, const float* lossy_poses, uint32_t num_samples, uint32_t num_tracks,
+	float sample_rate, float duration, const uint32_t* parent_indices, const float* shell_distances, int normalize_mode,
+	aclo_track_error* out_error, float* out_errors, float* scratch_object_poses);
+int aclo_scalar_track_error(const float* raw_values, const float* lossy_values, uint32_t num_samples, uint32_t num_tracks, uint32_t components,
+	float sample_rate, float duration, aclo_track_error* out_error);
+
 /* Single-threaded timing helper for the "port" CPU baseline: decodes `num_requests` (clip, time)
  * requests with default settings and returns the elapsed seconds. */
 double aclo_bench_transform(const void* const* blobs, const uint32_t* request_clip, const float* request_time,

@@ -228,3 +228,59 @@ def bench_transform(blobs, request_clip, request_time, max_tracks: int) -> float
     request_time = np.ascontiguousarray(request_time, dtype=np.float32)
     return float(lib().aclo_bench_transform(C.cast(ptrs, C.c_void_p), request_clip.ctypes.data, request_time.ctypes.data,
                                             request_clip.size, max_tracks))
+
+
+# the compression error measurement over already sampled poses (acl_oracle.h)
+class TrackError(C.Structure):
+    _fields_ = [("index", C.c_uint32), ("error", C.c_float), ("sample_time", C.c_float)]
+
+
+NORMALIZE_RTM_SSE2, NORMALIZE_IEEE = 0, 1
+
+
+def local_to_object_space(local_pose: np.ndarray, parents: np.ndarray, normalize_mode: int = NORMALIZE_IEEE) -> np.ndarray:
+    """qvvf_transform_error_metric::local_to_object_space of one pose, float32 [num_tracks][12]."""
+    local_pose = np.ascontiguousarray(local_pose, dtype=np.float32)
+    parents = np.ascontiguousarray(parents, dtype=np.uint32)
+    out = np.zeros_like(local_pose)
+    fn = lib().aclo_local_to_object_space
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
+    rc = fn(local_pose.ctypes.data, parents.ctypes.data, local_pose.shape[0], normalize_mode, out.ctypes.data)
+    if rc < 0:
+        raise RuntimeError("aclo_local_to_object_space: a parent does not precede its child")
+    return out
+
+
+def transform_track_error(raw_poses: np.ndarray, lossy_poses: np.ndarray, sample_rate: float, duration: float, parents: np.ndarray,
+                          shell_distances: np.ndarray, normalize_mode: int = NORMALIZE_IEEE):
+    """The loop of calculate_transform_track_error over [num_samples][num_tracks][12] poses.
+    Returns (TrackError, errors float32 [num_samples][num_tracks], negative_scale_seen)."""
+    raw_poses = np.ascontiguousarray(raw_poses, dtype=np.float32)
+    lossy_poses = np.ascontiguousarray(lossy_poses, dtype=np.float32)
+    parents = np.ascontiguousarray(parents, dtype=np.uint32)
+    shell_distances = np.ascontiguousarray(shell_distances, dtype=np.float32)
+    num_samples, num_tracks = raw_poses.shape[0], raw_poses.shape[1]
+    assert lossy_poses.shape == raw_poses.shape and raw_poses.shape[2] == 12
+    errors = np.zeros((num_samples, num_tracks), dtype=np.float32)
+    scratch = np.zeros((2, max(num_tracks, 1), 12), dtype=np.float32)
+    result = TrackError()
+    fn = lib().aclo_transform_track_error
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
+                   C.POINTER(TrackError), C.c_void_p, C.c_void_p]
+    rc = fn(raw_poses.ctypes.data, lossy_poses.ctypes.data, num_samples, num_tracks, sample_rate, duration, parents.ctypes.data,
+            shell_distances.ctypes.data, normalize_mode, C.byref(result), errors.ctypes.data, scratch.ctypes.data)
+    if rc < 0:
+        raise RuntimeError("aclo_transform_track_error: a parent does not precede its child")
+    return result, errors, rc == 1
+
+
+def scalar_track_error(raw_values: np.ndarray, lossy_values: np.ndarray, components: int, sample_rate: float, duration: float) -> TrackError:
+    """calculate_scalar_track_error over [num_samples][num_tracks][4] rows (the first `components` floats of each row count)."""
+    raw_values = np.ascontiguousarray(raw_values, dtype=np.float32)
+    lossy_values = np.ascontiguousarray(lossy_values, dtype=np.float32)
+    assert raw_values.shape == lossy_values.shape and raw_values.shape[2] == 4
+    result = TrackError()
+    fn = lib().aclo_scalar_track_error
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.POINTER(TrackError)]
+    fn(raw_values.ctypes.data, lossy_values.ctypes.data, raw_values.shape[0], raw_values.shape[1], components, sample_rate, duration, C.byref(result))
+    return result

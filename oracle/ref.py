@@ -309,3 +309,66 @@ def usable_threads() -> int:
         except (OSError, ValueError, IndexError):
             continue
     return max(1, threads)
+
+
+# the reference's calculate_compression_error and the values it works on (oracle/ref_tool.cpp)
+class TrackError(C.Structure):
+    _fields_ = [("index", C.c_uint32), ("error", C.c_float), ("sample_time", C.c_float)]
+
+
+def finite_duration(num_samples: int, sample_rate: float) -> float:
+    """calculate_finite_duration (core/impl/time_utils.impl.h:105-114) of a raw clip, in float arithmetic like the reference."""
+    if num_samples <= 1:
+        return 0.0
+    return float(np.float32(num_samples - 1) / np.float32(sample_rate))
+
+
+def transform_error(spec: TransformSpec, blob: np.ndarray, settings: int = SETTINGS_DEBUG) -> dict:
+    """calculate_compression_error(allocator, raw clip of `spec`, decompression_context<settings>(blob), qvvf_transform_error_metric).
+    Returns the track_error plus the function's inputs and intermediates recomputed with the reference's own classes:
+    raw_poses / lossy_poses float32 [num_samples][num_tracks][12], object_poses [2][num_samples][num_tracks][12],
+    errors [num_samples][num_tracks], parents uint32 [num_tracks], shell_distances float32 [num_tracks], rounding."""
+    n, m = spec.num_tracks, spec.num_samples
+    out = dict(raw_poses=np.zeros((m, n, 12), np.float32), lossy_poses=np.zeros((m, n, 12), np.float32),
+               object_poses=np.zeros((2, m, n, 12), np.float32), errors=np.zeros((m, n), np.float32),
+               parents=np.zeros(n, np.uint32), shell_distances=np.zeros(n, np.float32))
+    result, rounding = TrackError(), C.c_uint32()
+    fn = lib().aclref_transform_error
+    fn.argtypes = [C.POINTER(_TransformSpec), C.c_void_p, C.c_uint32, C.POINTER(TrackError), C.POINTER(C.c_uint32)] + [C.c_void_p] * 6
+    c_spec = spec.to_c()
+    rc = fn(C.byref(c_spec), blob.ctypes.data, settings, C.byref(result), C.byref(rounding), out["raw_poses"].ctypes.data,
+            out["lossy_poses"].ctypes.data, out["object_poses"].ctypes.data, out["errors"].ctypes.data, out["parents"].ctypes.data,
+            out["shell_distances"].ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"aclref_transform_error failed ({rc})")
+    out.update(index=int(result.index), error=float(result.error), sample_time=float(result.sample_time), rounding=int(rounding.value),
+               sample_rate=float(spec.sample_rate), duration=finite_duration(m, spec.sample_rate))
+    return out
+
+
+def scalar_error(spec: ScalarSpec, blob: np.ndarray) -> dict:
+    """calculate_compression_error(allocator, raw clip of `spec`, decompression_context<default_scalar>(blob)) + the raw samples
+    float32 [num_samples][num_tracks][4] it compares with."""
+    raw = np.zeros((spec.num_samples, spec.num_tracks, 4), np.float32)
+    result, rounding = TrackError(), C.c_uint32()
+    fn = lib().aclref_scalar_error
+    fn.argtypes = [C.POINTER(_ScalarSpec), C.c_void_p, C.POINTER(TrackError), C.POINTER(C.c_uint32), C.c_void_p]
+    c_spec = spec.to_c()
+    rc = fn(C.byref(c_spec), blob.ctypes.data, C.byref(result), C.byref(rounding), raw.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"aclref_scalar_error failed ({rc})")
+    return dict(index=int(result.index), error=float(result.error), sample_time=float(result.sample_time), rounding=int(rounding.value),
+                raw_values=raw, sample_rate=float(spec.sample_rate), duration=finite_duration(spec.num_samples, spec.sample_rate))
+
+
+def bench_transform_error(spec: TransformSpec, blobs: list[np.ndarray], num_threads: int) -> tuple[float, np.ndarray]:
+    """Seconds the reference's calculate_compression_error takes for clips spec.seed .. spec.seed + len(blobs) - 1 on `num_threads`
+    host threads (raw clips rebuilt outside the timed region), and the per clip (index, error, sample_time) records."""
+    ptrs = (C.c_void_p * len(blobs))(*[b.ctypes.data for b in blobs])
+    errors = np.zeros(len(blobs), dtype=np.dtype([("index", np.uint32), ("error", np.float32), ("sample_time", np.float32)]))
+    fn = lib().aclref_bench_transform_error
+    fn.restype = C.c_double
+    fn.argtypes = [C.POINTER(_TransformSpec), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    c_spec = spec.to_c()
+    seconds = float(fn(C.byref(c_spec), C.cast(ptrs, C.c_void_p), len(blobs), num_threads, errors.ctypes.data))
+    return seconds, errors

@@ -7,7 +7,9 @@
 //   (2) decompress with the reference decompression_context
 //       (includes/acl/decompression/decompress.h:76-201) to produce golden outputs,
 //   (3) expose the reference's seek() integers (key frames, segment bit offsets, alpha),
-//   (4) time the reference's CPU path on N host threads (bench.py --impl reference).
+//   (4) time the reference's CPU path on N host threads (bench.py --impl reference),
+//   (5) run the reference's calculate_compression_error (compression/impl/track_error.impl.h:400-571) and expose the
+//       values it works on (raw poses, lossy poses, per bone object space error) for the SURVEY 8(f1) parity tests.
 //
 // It is compiled from the reference headers where they lie (/root/reference) by oracle/Makefile into
 // oracle/_ref/libaclref.so (git-ignored, ships to the GPU box as a prebuilt file). No reference
@@ -18,6 +20,7 @@
 #include <acl/core/compressed_tracks.h>
 #include <acl/compression/compress.h>
 #include <acl/compression/track_array.h>
+#include <acl/compression/track_error.h>
 #include <acl/compression/transform_error_metrics.h>
 #include <acl/decompression/decompress.h>
 
@@ -137,14 +140,14 @@ namespace
 		return rtm::quat_normalize(q);
 	}
 
-	error_result build_transform_clip(const aclref_transform_spec& spec, compressed_tracks*& out_tracks)
+	// The raw clip of a spec (deterministic: the error metric harness below rebuilds the very clip that was compressed)
+	void make_transform_tracks(const aclref_transform_spec& spec, track_array_qvvf& track_list)
 	{
 		iallocator& alloc = allocator();
 		const uint32_t num_tracks = spec.num_tracks;
 		const uint32_t num_samples = spec.num_samples;
 		const float sample_rate = spec.sample_rate;
 
-		track_array_qvvf track_list(alloc, num_tracks);
 		rng_t rng(spec.seed);
 
 		const double two_pi = 6.283185307179586;
@@ -270,6 +273,13 @@ namespace
 
 			track_list[bone] = std::move(track);
 		}
+	}
+
+	error_result build_transform_clip(const aclref_transform_spec& spec, compressed_tracks*& out_tracks)
+	{
+		iallocator& alloc = allocator();
+		track_array_qvvf track_list(alloc, spec.num_tracks);
+		make_transform_tracks(spec, track_list);
 
 		qvvf_transform_error_metric error_metric;
 
@@ -870,5 +880,220 @@ extern "C"
 			free(blobs[clip]);
 		}
 		return ok ? offset : 0;
+	}
+	//////////////////////////////////////////////////////////////////////////
+	// calculate_compression_error
+
+	// acl::track_error (compression/track_error.h:48-66)
+	struct aclref_track_error
+	{
+		uint32_t index;
+		float    error;
+		float    sample_time;
+	};
+
+	// The unmodified calculate_compression_error(allocator, raw_tracks, context, qvvf_transform_error_metric)
+	// (track_error.impl.h:465-571 -> calculate_transform_track_error :225-392) on the raw clip of `spec` against `blob` (what
+	// aclref_compress_transform(spec) returned), with decompression_context<settings_kind 0 default / 1 debug>. Every other
+	// output is optional and exposes what that function works on, recomputed with the reference's own classes the way its loop does:
+	//   out_rounding    the rounding policy it seeks with (nearest, or none for stripped / database clips, :556-559)
+	//   out_raw_poses   [num_samples][num_tracks][12]  raw_tracks.sample_tracks(sample_time, rounding, writer)
+	//   out_lossy_poses [num_samples][num_tracks][12]  seek + decompress_tracks into a debug_track_writer initialised with the bind pose
+	//   out_object_poses[2][num_samples][num_tracks][12] error_metric.local_to_object_space of both
+	//   out_errors      [num_samples][num_tracks]      error_metric.calculate_error per bone
+	//   out_parents / out_shell_distances [num_tracks] track_desc_transformf::parent_index / shell_distance
+}	// extern "C"
+
+namespace
+{
+	template<class settings_type>
+	int transform_error_impl(const aclref_transform_spec& spec, const compressed_tracks& tracks, aclref_track_error* out_error, uint32_t* out_rounding,
+		float* out_raw_poses, float* out_lossy_poses, float* out_object_poses, float* out_errors, uint32_t* out_parents, float* out_shell_distances)
+	{
+		iallocator& alloc = allocator();
+		track_array_qvvf raw_tracks(alloc, spec.num_tracks);
+		make_transform_tracks(spec, raw_tracks);
+
+		decompression_context<settings_type> context;
+		if (!context.initialize(tracks))
+			return -1;
+
+		const qvvf_transform_error_metric error_metric;
+		const track_error result = calculate_compression_error(alloc, raw_tracks, context, error_metric);
+		out_error->index = result.index;
+		out_error->error = result.error;
+		out_error->sample_time = result.sample_time;
+
+		const sample_rounding_policy rounding = (tracks.has_database() || tracks.has_stripped_keyframes()) ? sample_rounding_policy::none : sample_rounding_policy::nearest;
+		if (out_rounding != nullptr)
+			*out_rounding = uint32_t(rounding);
+
+		const uint32_t num_tracks = raw_tracks.get_num_tracks();
+		const uint32_t num_samples = raw_tracks.get_num_samples_per_track();
+		const float sample_rate = raw_tracks.get_sample_rate();
+		const float duration = raw_tracks.get_finite_duration();
+
+		std::vector<uint32_t> parents(num_tracks), self(num_tracks);
+		for (uint32_t bone = 0; bone < num_tracks; ++bone)
+		{
+			const track_desc_transformf& desc = raw_tracks[bone].get_description();
+			parents[bone] = desc.parent_index;
+			self[bone] = bone;
+			if (out_parents != nullptr) out_parents[bone] = desc.parent_index;
+			if (out_shell_distances != nullptr) out_shell_distances[bone] = desc.shell_distance;
+		}
+
+		acl_impl::debug_track_writer raw_writer(alloc, track_type8::qvvf, num_tracks);
+		acl_impl::debug_track_writer lossy_writer(alloc, track_type8::qvvf, num_tracks);
+		lossy_writer.initialize_with_defaults(raw_tracks);
+		std::vector<rtm::qvvf> raw_object(num_tracks), lossy_object(num_tracks);
+
+		itransform_error_metric::local_to_object_space_args object_args;
+		object_args.dirty_transform_indices = self.data();
+		object_args.num_dirty_transforms = num_tracks;
+		object_args.parent_transform_indices = parents.data();
+		object_args.num_transforms = num_tracks;
+
+		for (uint32_t sample = 0; sample < num_samples; ++sample)
+		{
+			const float sample_time = rtm::scalar_min(float(sample) / sample_rate, duration);
+			raw_tracks.sample_tracks(sample_time, rounding, raw_writer);
+			context.seek(sample_time, rounding);
+			context.decompress_tracks(lossy_writer);
+
+			object_args.local_transforms = raw_writer.tracks_typed.qvvf;
+			error_metric.local_to_object_space(object_args, raw_object.data());
+			object_args.local_transforms = lossy_writer.tracks_typed.qvvf;
+			error_metric.local_to_object_space(object_args, lossy_object.data());
+
+			const size_t pose_floats = size_t(num_tracks) * 12;
+			if (out_raw_poses != nullptr) std::memcpy(out_raw_poses + sample * pose_floats, raw_writer.tracks_typed.qvvf, pose_floats * sizeof(float));
+			if (out_lossy_poses != nullptr) std::memcpy(out_lossy_poses + sample * pose_floats, lossy_writer.tracks_typed.qvvf, pose_floats * sizeof(float));
+			if (out_object_poses != nullptr)
+			{
+				std::memcpy(out_object_poses + sample * pose_floats, raw_object.data(), pose_floats * sizeof(float));
+				std::memcpy(out_object_poses + (size_t(num_samples) + sample) * pose_floats, lossy_object.data(), pose_floats * sizeof(float));
+			}
+			if (out_errors != nullptr)
+				for (uint32_t bone = 0; bone < num_tracks; ++bone)
+				{
+					itransform_error_metric::calculate_error_args error_args;
+					error_args.transform0 = &raw_object[bone];
+					error_args.transform1 = &lossy_object[bone];
+					error_args.construct_sphere_shell(raw_tracks[bone].get_description().shell_distance);
+					out_errors[size_t(sample) * num_tracks + bone] = rtm::scalar_cast(error_metric.calculate_error(error_args));
+				}
+		}
+		return 0;
+	}
+
+}
+
+extern "C"
+{
+	int aclref_transform_error(const aclref_transform_spec* spec, const void* blob, uint32_t settings_kind, aclref_track_error* out_error, uint32_t* out_rounding,
+		float* out_raw_poses, float* out_lossy_poses, float* out_object_poses, float* out_errors, uint32_t* out_parents, float* out_shell_distances)
+	{
+		const compressed_tracks& tracks = *static_cast<const compressed_tracks*>(blob);
+		if (tracks.get_track_type() != track_type8::qvvf || tracks.get_num_tracks() != spec->num_tracks)
+			return -2;
+		if (settings_kind == 0)
+			return transform_error_impl<settings_default>(*spec, tracks, out_error, out_rounding, out_raw_poses, out_lossy_poses, out_object_poses, out_errors, out_parents, out_shell_distances);
+		return transform_error_impl<settings_debug>(*spec, tracks, out_error, out_rounding, out_raw_poses, out_lossy_poses, out_object_poses, out_errors, out_parents, out_shell_distances);
+	}
+
+	// The scalar flavour: calculate_compression_error(allocator, raw_tracks, context) (track_error.impl.h:400-463 -> calculate_scalar_track_error
+	// :166-223). out_raw_values [num_samples][num_tracks][4] = raw_tracks.sample_tracks(...) (first N components of each row).
+	int aclref_scalar_error(const aclref_scalar_spec* spec, const void* blob, aclref_track_error* out_error, uint32_t* out_rounding, float* out_raw_values)
+	{
+		iallocator& alloc = allocator();
+		const compressed_tracks& tracks = *static_cast<const compressed_tracks*>(blob);
+		if (tracks.get_track_type() == track_type8::qvvf || tracks.get_num_tracks() != spec->num_tracks)
+			return -2;
+
+		track_array raw_tracks;
+		switch (static_cast<track_type8>(spec->track_type))
+		{
+		case track_type8::float1f: { track_array_float1f list(alloc, spec->num_tracks); fill_scalar_tracks<track_float1f, float, 1>(*spec, list); raw_tracks = std::move(list); break; }
+		case track_type8::float2f: { track_array_float2f list(alloc, spec->num_tracks); fill_scalar_tracks<track_float2f, rtm::float2f, 2>(*spec, list); raw_tracks = std::move(list); break; }
+		case track_type8::float3f: { track_array_float3f list(alloc, spec->num_tracks); fill_scalar_tracks<track_float3f, rtm::float3f, 3>(*spec, list); raw_tracks = std::move(list); break; }
+		case track_type8::float4f: { track_array_float4f list(alloc, spec->num_tracks); fill_scalar_tracks<track_float4f, rtm::float4f, 4>(*spec, list); raw_tracks = std::move(list); break; }
+		case track_type8::vector4f: { track_array_vector4f list(alloc, spec->num_tracks); fill_scalar_tracks<track_vector4f, rtm::vector4f, 4>(*spec, list); raw_tracks = std::move(list); break; }
+		default: return -3;
+		}
+
+		decompression_context<default_scalar_decompression_settings> context;
+		if (!context.initialize(tracks))
+			return -1;
+		const track_error result = calculate_compression_error(alloc, raw_tracks, context);
+		out_error->index = result.index;
+		out_error->error = result.error;
+		out_error->sample_time = result.sample_time;
+
+		const sample_rounding_policy rounding = (tracks.has_database() || tracks.has_stripped_keyframes()) ? sample_rounding_policy::none : sample_rounding_policy::nearest;
+		if (out_rounding != nullptr)
+			*out_rounding = uint32_t(rounding);
+		if (out_raw_values != nullptr)
+		{
+			const uint32_t num_tracks = raw_tracks.get_num_tracks();
+			const uint32_t num_samples = raw_tracks.get_num_samples_per_track();
+			scalar_writer writer;
+			for (uint32_t sample = 0; sample < num_samples; ++sample)
+			{
+				const float sample_time = rtm::scalar_min(float(sample) / raw_tracks.get_sample_rate(), raw_tracks.get_finite_duration());
+				writer.out = out_raw_values + size_t(sample) * num_tracks * 4;
+				raw_tracks.sample_tracks(sample_time, rounding, writer);
+			}
+		}
+		return 0;
+	}
+
+	// CPU baseline of the 8(f1) workload: calculate_compression_error of clips spec.seed .. spec.seed + num_clips - 1 (their blobs in `blobs`),
+	// clips dealt to `num_threads` threads. The raw clips are rebuilt before the clock starts; only the error measurement is timed.
+	// Returns elapsed seconds; out_errors (optional) receives one aclref_track_error per clip.
+	double aclref_bench_transform_error(const aclref_transform_spec* spec, const void* const* blobs, uint32_t num_clips, uint32_t num_threads, aclref_track_error* out_errors)
+	{
+		if (num_threads == 0)
+			num_threads = 1;
+		iallocator& alloc = allocator();
+		std::vector<track_array_qvvf> raw_clips;
+		raw_clips.reserve(num_clips);
+		for (uint32_t clip = 0; clip < num_clips; ++clip)
+		{
+			aclref_transform_spec clip_spec = *spec;
+			clip_spec.seed = spec->seed + clip;
+			raw_clips.emplace_back(alloc, clip_spec.num_tracks);
+			make_transform_tracks(clip_spec, raw_clips.back());
+		}
+
+		std::atomic<uint32_t> next(0);
+		std::vector<std::thread> threads;
+		const auto start = std::chrono::steady_clock::now();
+		for (uint32_t thread_index = 0; thread_index < num_threads; ++thread_index)
+		{
+			threads.emplace_back([&]()
+			{
+				const qvvf_transform_error_metric error_metric;
+				for (;;)
+				{
+					const uint32_t clip = next.fetch_add(1);
+					if (clip >= num_clips)
+						break;
+					decompression_context<settings_debug> context;
+					if (!context.initialize(*static_cast<const compressed_tracks*>(blobs[clip])))
+						continue;
+					const track_error result = calculate_compression_error(alloc, raw_clips[clip], context, error_metric);
+					if (out_errors != nullptr)
+					{
+						out_errors[clip].index = result.index;
+						out_errors[clip].error = result.error;
+						out_errors[clip].sample_time = result.sample_time;
+					}
+				}
+			});
+		}
+		for (std::thread& thread : threads)
+			thread.join();
+		return std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
 	}
 }
