@@ -723,7 +723,7 @@ extern "C"
 			p.keys = d_keys;
 			p.flags = d_flags;
 			p.error_matrix = d_out_error_matrix;
-			p.error_stride = clipset->info.max_tracks;
+			p.error_stride = uint32_t(stride / bone_stride);		// tracks a pose row holds: every job fits (checked above)
 			p.plane_stride = plane_stride;
 			p.components = components;
 

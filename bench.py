@@ -609,6 +609,11 @@ def main() -> None:
         workloads = {}
         for name in ("c3", "c5", "c4"):
             workloads[name] = extra_workload(name, torch, ab, ctx, local_rank, peak, barrier)
+        if w["distinct"]:
+            try:
+                workloads["error_metric"] = error_metric_workload(torch, ab, ctx, w, clipset, local_rank, peak, barrier)
+            except Exception as failure:      # an extra block must not take the headline line down with it; it is reported, not hidden
+                workloads["error_metric"] = {"failed": f"{type(failure).__name__}: {failure}"}
 
     result = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -670,6 +675,78 @@ def extra_workload(name: str, torch, ab, ctx, local_rank: int, peak: float, barr
            "clocks": clocks}
     clipset.release()
     return out
+
+
+def error_metric_workload(torch, ab, ctx, w, clipset, local_rank: int, peak: float, barrier, num_clips: int = 4096) -> dict:
+    """SURVEY 8(f1): acl::calculate_compression_error (decode every sample of a clip, object space, qvvf_transform_error_metric against the
+    raw poses, worst track) for the first `num_clips` clips of the C2 clip set in ONE call, poses never leaving the GPU. Unit: bone-poses
+    MEASURED per second. The CPU figure next to it is the unmodified reference's calculate_compression_error on a bounded sample."""
+    from oracle import ref
+    num_clips = min(num_clips, w["num_clips"])
+    spec = ref.TransformSpec(num_tracks=w["num_tracks"], num_samples=60, seed=2000)
+    t0 = time.time()
+    raw, parents, shells = ref.sample_raw_transform_batch(spec, num_clips)
+    log(f"[bench] error metric: raw poses of {num_clips} clips in {time.time() - t0:.1f} s ({raw.nbytes / 1e6:.0f} MB)")
+    num_samples, num_tracks = raw.shape[1], raw.shape[2]
+    jobs = np.zeros(num_clips, dtype=ab.ERROR_JOB_DTYPE)
+    jobs["clip"] = np.arange(num_clips)
+    jobs["num_samples"] = num_samples
+    jobs["sample_rate"] = spec.sample_rate
+    jobs["duration"] = ref.finite_duration(num_samples, spec.sample_rate)
+    jobs["num_tracks"] = num_tracks
+    jobs["first_raw_pose"] = np.arange(num_clips, dtype=np.uint64) * num_samples
+    d_raw = torch.from_numpy(raw.reshape(-1)).cuda()
+    d_parents = torch.from_numpy(parents.view(np.int32)).cuda()
+    d_shells = torch.from_numpy(shells).cuda()
+    d_errors = torch.zeros(num_clips * 4, dtype=torch.int32, device="cuda")
+    # what tools/acl_compressor measures with: debug_transform_decompression_settings, bind pose = identity
+    options = ab.Options(normalization=ab.NORMALIZE_ALWAYS, per_track_rounding=1, multiple_rotation_formats=1, default_modes=(ab.DEFAULT_CONSTANT,) * 3,
+                         constant_defaults=[0, 0, 0, 1, 0, 0, 0, 0, 1, 1, 1, 0])
+    stream = torch.cuda.current_stream()
+
+    def launch():
+        ctx.calculate_compression_error(clipset, jobs, d_raw, d_parents, d_shells, options, d_errors, stream=stream)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches_before = ctx.launch_count
+    launch()
+    launches_per_call = ctx.launch_count - launches_before
+    torch.cuda.synchronize()
+    probe0, probe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    probe0.record(stream); launch(); probe1.record(stream); torch.cuda.synchronize()
+    steps = int(min(200, max(10, 60.0 / max(probe0.elapsed_time(probe1), 1e-3))))
+    elapsed_ms, call_ms = time_launches(torch, launch, stream, steps, 3, barrier, sampler)
+    clocks = sampler.stop()
+    errors = d_errors.cpu().numpy().view(ab.TRACK_ERROR_DTYPE)
+
+    units = num_clips * num_samples * num_tracks
+    compressed = int(w["sizes"][:num_clips].astype(np.int64).sum())
+    alg_in = compressed + raw.nbytes + parents.nbytes + shells.nbytes
+    alg_out = 16 * num_clips
+    achieved = (alg_in + alg_out) / (call_ms * 1e-3) / 1e9
+
+    # the unmodified reference on the host threads, a bounded sample of the same clips; its worst tracks must be the GPU's
+    threads = ref.usable_threads()
+    sample = int(min(num_clips, max(threads * 8, 64)))
+    blobs = host_blobs(w)[:sample]
+    seconds, cpu_errors = ref.bench_transform_error(spec, blobs, threads)
+    single_sample = int(min(sample, 64))
+    single_seconds, _ = ref.bench_transform_error(spec, blobs[:single_sample], 1)
+    worst = float(np.max(np.abs(errors["error"][:sample] - cpu_errors["error"])))
+    same_track = float(np.mean(errors["index"][:sample] == cpu_errors["index"]))
+    del d_raw
+    return {"workload": f"8(f1): calculate_compression_error of {num_clips} clips x {num_tracks} bones x {num_samples} samples in one call "
+                        "(decode every sample + object space + qvvf_transform_error_metric + worst track per clip)",
+            "value": units * steps / (elapsed_ms * 1e-3), "unit": "bone-poses measured/s", "steps": steps, "call_ms": call_ms, "launches_per_call": int(launches_per_call),
+            "roofline": {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "algorithmic_bytes_in": int(alg_in),
+                         "algorithmic_bytes_out": int(alg_out),
+                         "note": "algorithmic = compressed clips + raw poses (48 B per bone-pose) in, 16 B per clip out; the decoded poses are an intermediate "
+                                 "(written and read back once through L2 / HBM: about 2 x 48 B per bone-pose on top)"},
+            "cpu_baseline": {"value": sample * num_samples * num_tracks / seconds, "unit": "bone-poses measured/s", "cores": threads, "kind": "reference",
+                             "single_thread_value": single_sample * num_samples * num_tracks / single_seconds,
+                             "sample": f"{sample} of {num_clips} clips, acl::calculate_compression_error(debug settings, qvvf_transform_error_metric) on {threads} host threads"},
+            "parity_vs_cpu_sample": {"max_abs_error_difference": worst, "same_worst_track_fraction": same_track, "gate": 5e-5},
+            "flags_set": int(np.count_nonzero(errors["flags"])), "clocks": clocks}
 
 
 def routed_c5_job(args, torch, dist, ab, ctx, rank, local_rank, world, reducer, barrier, layout) -> dict:

@@ -280,7 +280,8 @@ typedef struct aclb200_error_job
  *   d_output_indices  device, optional: track_desc::output_index per raw track (0xFFFFFFFF = stripped from the compressed clip: the raw
  *                     value stands in, track_error.impl.h:522-532); NULL = every raw track i is output i
  *   d_out_errors      device: one aclb200_track_error per job
- *   d_out_error_matrix device, optional: the error of every bone of every pose, row (poses of the earlier jobs + s) of max_tracks floats
+ *   d_out_error_matrix device, optional: the error of every bone of every pose, row (poses of the earlier jobs + s) of
+ *                     pose_stride_bytes / 48 floats (= max_tracks by default; scalar clip sets: tracks per row)
  * No additive base (track_error.impl.h:573-680). rtm::quat_normalize's rsqrtss estimate is CPU specific: errors agree with a given CPU's
  * within 5e-5 on poses tens of units across, not bit for bit (see error_metric.cu). Asynchronous on `stream`; uses scratch owned by the context. */
 ACLB200_API aclb200_status aclb200_calculate_compression_error(aclb200_context* context, const aclb200_clipset* clipset, const aclb200_error_job* jobs,

@@ -372,3 +372,17 @@ def bench_transform_error(spec: TransformSpec, blobs: list[np.ndarray], num_thre
     c_spec = spec.to_c()
     seconds = float(fn(C.byref(c_spec), C.cast(ptrs, C.c_void_p), len(blobs), num_threads, errors.ctypes.data))
     return seconds, errors
+
+
+def sample_raw_transform_batch(spec: TransformSpec, num_clips: int, num_threads: int = 0):
+    """Raw poses of clips spec.seed .. spec.seed + num_clips - 1 as calculate_compression_error samples them (nearest):
+    (float32 [num_clips][num_samples][num_tracks][12], parents uint32 [num_tracks], shell_distances float32 [num_tracks])."""
+    raw = np.zeros((num_clips, spec.num_samples, spec.num_tracks, 12), np.float32)
+    parents, shells = np.zeros(spec.num_tracks, np.uint32), np.zeros(spec.num_tracks, np.float32)
+    fn = lib().aclref_sample_raw_transform_batch
+    fn.argtypes = [C.POINTER(_TransformSpec), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    c_spec = spec.to_c()
+    rc = fn(C.byref(c_spec), num_clips, num_threads or usable_threads(), raw.ctypes.data, parents.ctypes.data, shells.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("aclref_sample_raw_transform_batch failed")
+    return raw, parents, shells

@@ -1048,6 +1048,55 @@ extern "C"
 		return 0;
 	}
 
+	// The raw poses calculate_compression_error would sample for clips spec.seed .. spec.seed + num_clips - 1 (raw_tracks.sample_tracks at
+	// min(i / sample_rate, duration) with the `nearest` policy, track_error.impl.h:337-338; `none` gives the same poses at those times up to
+	// the interpolation's rounding, callers with stripped clips use aclref_transform_error instead), clips dealt to `num_threads` threads:
+	// out_raw_poses [num_clips][num_samples][num_tracks][12]. Also the skeleton of the (shared) rig: out_parents / out_shell_distances [num_tracks].
+	int aclref_sample_raw_transform_batch(const aclref_transform_spec* spec, uint32_t num_clips, uint32_t num_threads, float* out_raw_poses,
+		uint32_t* out_parents, float* out_shell_distances)
+	{
+		if (num_threads == 0)
+			num_threads = 1;
+		std::atomic<uint32_t> next(0);
+		std::vector<std::thread> threads;
+		for (uint32_t thread_index = 0; thread_index < num_threads; ++thread_index)
+		{
+			threads.emplace_back([&]()
+			{
+				iallocator& alloc = allocator();
+				acl_impl::debug_track_writer writer(alloc, track_type8::qvvf, spec->num_tracks);
+				for (;;)
+				{
+					const uint32_t clip = next.fetch_add(1);
+					if (clip >= num_clips)
+						break;
+					aclref_transform_spec clip_spec = *spec;
+					clip_spec.seed = spec->seed + clip;
+					track_array_qvvf raw_tracks(alloc, clip_spec.num_tracks);
+					make_transform_tracks(clip_spec, raw_tracks);
+					const uint32_t num_samples = raw_tracks.get_num_samples_per_track();
+					const size_t pose_floats = size_t(clip_spec.num_tracks) * 12;
+					for (uint32_t sample = 0; sample < num_samples; ++sample)
+					{
+						const float sample_time = rtm::scalar_min(float(sample) / raw_tracks.get_sample_rate(), raw_tracks.get_finite_duration());
+						raw_tracks.sample_tracks(sample_time, sample_rounding_policy::nearest, writer);
+						std::memcpy(out_raw_poses + (size_t(clip) * num_samples + sample) * pose_floats, writer.tracks_typed.qvvf, pose_floats * sizeof(float));
+					}
+					if (clip == 0)
+						for (uint32_t bone = 0; bone < clip_spec.num_tracks; ++bone)
+						{
+							const track_desc_transformf& desc = raw_tracks[bone].get_description();
+							if (out_parents != nullptr) out_parents[bone] = desc.parent_index;
+							if (out_shell_distances != nullptr) out_shell_distances[bone] = desc.shell_distance;
+						}
+				}
+			});
+		}
+		for (std::thread& thread : threads)
+			thread.join();
+		return 0;
+	}
+
 	// CPU baseline of the 8(f1) workload: calculate_compression_error of clips spec.seed .. spec.seed + num_clips - 1 (their blobs in `blobs`),
 	// clips dealt to `num_threads` threads. The raw clips are rebuilt before the clock starts; only the error measurement is timed.
 	// Returns elapsed seconds; out_errors (optional) receives one aclref_track_error per clip.
