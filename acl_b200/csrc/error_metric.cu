@@ -12,7 +12,8 @@
 // the warp takes 32 consecutive bones at a time and resolves them in wavefronts: a lane whose parent lies in an earlier chunk -- or was
 // finished by an earlier wavefront of this chunk -- computes, the others wait for the next wavefront (skeletons are shallow and bushy:
 // a handful of wavefronts per chunk). Object transforms live in shared memory as [component][bone] planes so that 32 lanes reading 32
-// different parents hit 32 different banks. Every float operation is the reference's, in its order, never fused (the library is built
+// different parents hit 32 different banks. The measurement itself (three shell points through both transforms) runs after the chunk's
+// wavefronts with every lane busy, and the raw and the lossy pose travel together as packed f32x2 values. Every float operation is the reference's, in its order, never fused (the library is built
 // with --fmad=false); the one exception is rtm::quat_normalize, whose SSE2 code starts from the CPU specific rsqrtss estimate
 // (external/rtm/includes/rtm/quatf.h:917-953) and cannot be reproduced bit for bit by anyone: the IEEE 1 / sqrt stands in for it
 // (the tests' CPU restatement has both; errors agree with the reference within 5e-5 on poses tens of units across, tests/test_gpu_error_metric.py).
@@ -20,6 +21,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 namespace aclb200
@@ -64,131 +66,194 @@ namespace aclb200
 			uint32_t error_stride;			// floats per row of the matrix
 			uint32_t plane_stride;			// floats per [component] plane of a warp's object transforms
 			uint32_t components;			// scalar clips
+			float    one;					// 1.0f the compiler cannot see (keeps the packed mul + add unfused)
 		};
 
 		// ---- the reference's float operations, spelled out so nothing can be contracted -------------------------------------------
-		__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
-		__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
-		__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+		// The measurement runs the SAME operation sequence on the raw and on the lossy pose: the two travel as one packed f32x2 value
+		// (x = raw, y = lossy) through mul.rn.f32x2 / fma.rn.f32x2, half the instructions of two scalar streams. ptxas contracts a packed
+		// mul + add into one FFMA2 even under --fmad=false, so the packed add is issued as fma(a, one, b) with `one` a run-time 1.0f
+		// (round(a * 1 + b) == round(a + b)), like pipeline.cu does. Signs: the reference xors sign masks into products and adds them;
+		// -(p) + q == q - p, p + -(q) == p - q and -(p) + -(q) == -(p + q) hold exactly in IEEE arithmetic, so the sums below are written
+		// with subtractions and no negation (a packed operand has no free negate modifier).
+		template<class V> struct Fp;
 
-		struct Quat { float x, y, z, w; };
-		struct Vec3 { float x, y, z; };
-		struct Qvv { Quat rotation; Vec3 translation; Vec3 scale; };
-
-		// rtm::quat_mul, external/rtm/includes/rtm/quatf.h:498-545 (SSE2 path: the signs are xor-ed into the products)
-		__device__ __forceinline__ Quat quat_mul(const Quat& l, const Quat& r)
+		template<> struct Fp<float>
 		{
-			Quat out;
-			out.x = add(add(mul(r.w, l.x), mul(r.x, l.w)), add(mul(r.y, l.z), -mul(r.z, l.y)));
-			out.y = add(add(mul(r.w, l.y), -mul(r.x, l.z)), add(mul(r.y, l.w), mul(r.z, l.x)));
-			out.z = add(add(mul(r.w, l.z), mul(r.x, l.y)), add(-mul(r.y, l.x), mul(r.z, l.w)));
-			out.w = add(add(mul(r.w, l.w), -mul(r.x, l.x)), add(-mul(r.y, l.y), -mul(r.z, l.z)));
+			float one;
+			__device__ __forceinline__ float mul(float a, float b) const { return __fmul_rn(a, b); }
+			__device__ __forceinline__ float add(float a, float b) const { return __fadd_rn(a, b); }
+			__device__ __forceinline__ float sub(float a, float b) const { return __fsub_rn(a, b); }
+			__device__ __forceinline__ float splat(float a) const { return a; }
+			__device__ __forceinline__ float inv_sqrt(float a) const { return __fdiv_rn(1.0f, __fsqrt_rn(a)); }
+			__device__ __forceinline__ bool any_negative(float a, float b) const { return fminf(a, b) < 0.0f; }
+		};
+
+		template<> struct Fp<float2>
+		{
+			float one;
+			__device__ __forceinline__ float2 mul(float2 a, float2 b) const { return __fmul2_rn(a, b); }
+			__device__ __forceinline__ float2 add(float2 a, float2 b) const { return __ffma2_rn(a, make_float2(one, one), b); }
+			__device__ __forceinline__ float2 sub(float2 a, float2 b) const { return __ffma2_rn(b, make_float2(-one, -one), a); }
+			__device__ __forceinline__ float2 splat(float a) const { return make_float2(a, a); }
+			__device__ __forceinline__ float2 inv_sqrt(float2 a) const { return make_float2(__fdiv_rn(1.0f, __fsqrt_rn(a.x)), __fdiv_rn(1.0f, __fsqrt_rn(a.y))); }
+			__device__ __forceinline__ bool any_negative(float2 a, float2 b) const { return fminf(a.x, b.x) < 0.0f || fminf(a.y, b.y) < 0.0f; }
+		};
+
+		template<class V> struct Quat { V x, y, z, w; };
+		template<class V> struct Vec3 { V x, y, z; };
+		template<class V> struct Qvv { Quat<V> rotation; Vec3<V> translation; Vec3<V> scale; };
+
+		// rtm::quat_mul, external/rtm/includes/rtm/quatf.h:498-545 (SSE2 path): (rw*l + s0*(rx*l_wzyx)) + (s1*(ry*l_zwxy) + s2*(rz*l_yxwz))
+		template<class V>
+		__device__ __forceinline__ Quat<V> quat_mul(const Fp<V>& fp, const Quat<V>& l, const Quat<V>& r)
+		{
+			Quat<V> out;
+			out.x = fp.add(fp.add(fp.mul(r.w, l.x), fp.mul(r.x, l.w)), fp.sub(fp.mul(r.y, l.z), fp.mul(r.z, l.y)));
+			out.y = fp.add(fp.sub(fp.mul(r.w, l.y), fp.mul(r.x, l.z)), fp.add(fp.mul(r.y, l.w), fp.mul(r.z, l.x)));
+			out.z = fp.add(fp.add(fp.mul(r.w, l.z), fp.mul(r.x, l.y)), fp.sub(fp.mul(r.z, l.w), fp.mul(r.y, l.x)));
+			out.w = fp.sub(fp.sub(fp.mul(r.w, l.w), fp.mul(r.x, l.x)), fp.add(fp.mul(r.y, l.y), fp.mul(r.z, l.z)));
 			return out;
 		}
 
 		// rtm::quat_mul_vector3, quatf.h:616-668 (SSE2 path): temp = conjugate(r) * (v, 0) without its W terms, result = temp * r
-		__device__ __forceinline__ Vec3 quat_mul_vector3(const Vec3& v, const Quat& r)
+		template<class V>
+		__device__ __forceinline__ Vec3<V> quat_mul_vector3(const Fp<V>& fp, const Vec3<V>& v, const Quat<V>& r)
 		{
-			const float nx = -r.x, ny = -r.y, nz = -r.z;
-			const float t0 = add(add(mul(v.x, r.w), mul(v.y, nz)), mul(v.z, r.y));
-			const float t1 = add(add(mul(v.x, r.z), mul(v.y, r.w)), mul(v.z, nx));
-			const float t2 = add(add(mul(v.x, ny), mul(v.y, r.x)), mul(v.z, r.w));
-			const float t3 = add(add(mul(v.x, r.x), mul(v.y, r.y)), mul(v.z, r.z));
-			Vec3 out;
-			out.x = add(add(mul(r.w, t0), mul(r.x, t3)), add(mul(r.y, t2), mul(nz, t1)));
-			out.y = add(add(mul(r.w, t1), mul(nx, t2)), add(mul(r.y, t3), mul(r.z, t0)));
-			out.z = add(add(mul(r.w, t2), mul(r.x, t1)), add(mul(ny, t0), mul(r.z, t3)));
+			const V t0 = fp.add(fp.sub(fp.mul(v.x, r.w), fp.mul(v.y, r.z)), fp.mul(v.z, r.y));
+			const V t1 = fp.sub(fp.add(fp.mul(v.x, r.z), fp.mul(v.y, r.w)), fp.mul(v.z, r.x));
+			const V t2 = fp.add(fp.sub(fp.mul(v.y, r.x), fp.mul(v.x, r.y)), fp.mul(v.z, r.w));
+			const V t3 = fp.add(fp.add(fp.mul(v.x, r.x), fp.mul(v.y, r.y)), fp.mul(v.z, r.z));
+			Vec3<V> out;
+			out.x = fp.add(fp.add(fp.mul(r.w, t0), fp.mul(r.x, t3)), fp.sub(fp.mul(r.y, t2), fp.mul(r.z, t1)));
+			out.y = fp.add(fp.sub(fp.mul(r.w, t1), fp.mul(r.x, t2)), fp.add(fp.mul(r.y, t3), fp.mul(r.z, t0)));
+			out.z = fp.add(fp.add(fp.mul(r.w, t2), fp.mul(r.x, t1)), fp.sub(fp.mul(r.z, t3), fp.mul(r.y, t0)));
 			return out;
 		}
 
 		// rtm::quat_normalize, quatf.h:917-953: dot = (x2 + z2) + (y2 + w2); IEEE 1 / sqrt in place of the rsqrtss + 2 Newton-Raphson steps
-		__device__ __forceinline__ Quat quat_normalize(const Quat& q)
+		template<class V>
+		__device__ __forceinline__ Quat<V> quat_normalize(const Fp<V>& fp, const Quat<V>& q)
 		{
-			const float dot = add(add(mul(q.x, q.x), mul(q.z, q.z)), add(mul(q.y, q.y), mul(q.w, q.w)));
-			const float inv_len = __fdiv_rn(1.0f, __fsqrt_rn(dot));
-			Quat out;
-			out.x = mul(q.x, inv_len);
-			out.y = mul(q.y, inv_len);
-			out.z = mul(q.z, inv_len);
-			out.w = mul(q.w, inv_len);
+			const V dot = fp.add(fp.add(fp.mul(q.x, q.x), fp.mul(q.z, q.z)), fp.add(fp.mul(q.y, q.y), fp.mul(q.w, q.w)));
+			const V inv_len = fp.inv_sqrt(dot);
+			Quat<V> out;
+			out.x = fp.mul(q.x, inv_len);
+			out.y = fp.mul(q.y, inv_len);
+			out.z = fp.mul(q.z, inv_len);
+			out.w = fp.mul(q.w, inv_len);
 			return out;
 		}
 
 		// rtm::qvv_normalize(rtm::qvv_mul(local, parent_object)), external/rtm/includes/rtm/qvvf.h:315-355,426-430, positive scale branch.
 		// `negative` reports the case the reference sends through matrices (any min(lhs.scale, rhs.scale) component < 0).
-		__device__ __forceinline__ Qvv qvv_mul_normalize(const Qvv& local, const Qvv& parent, bool& negative)
+		template<class V>
+		__device__ __forceinline__ Qvv<V> qvv_mul_normalize(const Fp<V>& fp, const Qvv<V>& local, const Qvv<V>& parent, bool& negative)
 		{
-			negative = fminf(local.scale.x, parent.scale.x) < 0.0f || fminf(local.scale.y, parent.scale.y) < 0.0f || fminf(local.scale.z, parent.scale.z) < 0.0f;
-			Qvv out;
-			out.rotation = quat_normalize(quat_mul(local.rotation, parent.rotation));
-			Vec3 scaled;
-			scaled.x = mul(local.translation.x, parent.scale.x);
-			scaled.y = mul(local.translation.y, parent.scale.y);
-			scaled.z = mul(local.translation.z, parent.scale.z);
-			const Vec3 rotated = quat_mul_vector3(scaled, parent.rotation);
-			out.translation.x = add(rotated.x, parent.translation.x);
-			out.translation.y = add(rotated.y, parent.translation.y);
-			out.translation.z = add(rotated.z, parent.translation.z);
-			out.scale.x = mul(local.scale.x, parent.scale.x);
-			out.scale.y = mul(local.scale.y, parent.scale.y);
-			out.scale.z = mul(local.scale.z, parent.scale.z);
+			negative = fp.any_negative(local.scale.x, parent.scale.x) || fp.any_negative(local.scale.y, parent.scale.y) || fp.any_negative(local.scale.z, parent.scale.z);
+			Qvv<V> out;
+			out.rotation = quat_normalize(fp, quat_mul(fp, local.rotation, parent.rotation));
+			Vec3<V> scaled;
+			scaled.x = fp.mul(local.translation.x, parent.scale.x);
+			scaled.y = fp.mul(local.translation.y, parent.scale.y);
+			scaled.z = fp.mul(local.translation.z, parent.scale.z);
+			const Vec3<V> rotated = quat_mul_vector3(fp, scaled, parent.rotation);
+			out.translation.x = fp.add(rotated.x, parent.translation.x);
+			out.translation.y = fp.add(rotated.y, parent.translation.y);
+			out.translation.z = fp.add(rotated.z, parent.translation.z);
+			out.scale.x = fp.mul(local.scale.x, parent.scale.x);
+			out.scale.y = fp.mul(local.scale.y, parent.scale.y);
+			out.scale.z = fp.mul(local.scale.z, parent.scale.z);
 			return out;
 		}
 
-		// rtm::qvv_mul_point3, qvvf.h:370-373
-		__device__ __forceinline__ Vec3 qvv_mul_point3(const Vec3& point, const Qvv& qvv)
+		// rtm::qvv_mul_point3(shell point, qvv) (qvvf.h:370-373) for the three shell points of construct_sphere_shell
+		// (transform_error_metrics.h:261-266): (d, 0, 0), (0, d, 0), (0, 0, d). quat_mul_vector3 of a vector with two zero components: the
+		// terms that multiply a zero are dropped. They contribute +-0 to sums, which changes nothing but the sign of a sum that is itself
+		// zero, and the distance squares every difference: for finite transforms the measured error is bit-identical to the full sequence
+		// (a non-finite transform gives NaN there -- 0 * inf -- and may not here).
+		template<class V>
+		__device__ __forceinline__ void shell_points(const Fp<V>& fp, const Qvv<V>& q, float shell_distance, Vec3<V> out[3])
 		{
-			Vec3 scaled;
-			scaled.x = mul(qvv.scale.x, point.x);
-			scaled.y = mul(qvv.scale.y, point.y);
-			scaled.z = mul(qvv.scale.z, point.z);
-			const Vec3 rotated = quat_mul_vector3(scaled, qvv.rotation);
-			Vec3 out;
-			out.x = add(rotated.x, qvv.translation.x);
-			out.y = add(rotated.y, qvv.translation.y);
-			out.z = add(rotated.z, qvv.translation.z);
-			return out;
-		}
-
-		// rtm::vector_distance3_as_scalar, vector4f.h:2260-2264 (dot3 = (x2 + y2) + z2, :1899-1906; sqrtss)
-		__device__ __forceinline__ float distance3(const Vec3& a, const Vec3& b)
-		{
-			const float dx = sub(a.x, b.x), dy = sub(a.y, b.y), dz = sub(a.z, b.z);
-			return __fsqrt_rn(add(add(mul(dx, dx), mul(dy, dy)), mul(dz, dz)));
+			const Quat<V>& r = q.rotation;
+			const V d = fp.splat(shell_distance);
+			{
+				const V a = fp.mul(q.scale.x, d);
+				const V t0 = fp.mul(a, r.w), t1 = fp.mul(a, r.z), u2 = fp.mul(a, r.y), t3 = fp.mul(a, r.x);		// t2 = -u2
+				out[0].x = fp.add(fp.sub(fp.add(fp.mul(r.w, t0), fp.mul(r.x, t3)), fp.add(fp.mul(r.y, u2), fp.mul(r.z, t1))), q.translation.x);
+				out[0].y = fp.add(fp.add(fp.add(fp.mul(r.w, t1), fp.mul(r.x, u2)), fp.add(fp.mul(r.y, t3), fp.mul(r.z, t0))), q.translation.y);
+				out[0].z = fp.add(fp.add(fp.sub(fp.mul(r.x, t1), fp.mul(r.w, u2)), fp.sub(fp.mul(r.z, t3), fp.mul(r.y, t0))), q.translation.z);
+			}
+			{
+				const V b = fp.mul(q.scale.y, d);
+				const V u0 = fp.mul(b, r.z), t1 = fp.mul(b, r.w), t2 = fp.mul(b, r.x), t3 = fp.mul(b, r.y);		// t0 = -u0
+				out[1].x = fp.add(fp.add(fp.sub(fp.mul(r.x, t3), fp.mul(r.w, u0)), fp.sub(fp.mul(r.y, t2), fp.mul(r.z, t1))), q.translation.x);
+				out[1].y = fp.add(fp.add(fp.sub(fp.mul(r.w, t1), fp.mul(r.x, t2)), fp.sub(fp.mul(r.y, t3), fp.mul(r.z, u0))), q.translation.y);
+				out[1].z = fp.add(fp.add(fp.add(fp.mul(r.w, t2), fp.mul(r.x, t1)), fp.add(fp.mul(r.z, t3), fp.mul(r.y, u0))), q.translation.z);
+			}
+			{
+				const V c = fp.mul(q.scale.z, d);
+				const V t0 = fp.mul(c, r.y), u1 = fp.mul(c, r.x), t2 = fp.mul(c, r.w), t3 = fp.mul(c, r.z);		// t1 = -u1
+				out[2].x = fp.add(fp.add(fp.add(fp.mul(r.w, t0), fp.mul(r.x, t3)), fp.add(fp.mul(r.y, t2), fp.mul(r.z, u1))), q.translation.x);
+				out[2].y = fp.add(fp.sub(fp.add(fp.mul(r.y, t3), fp.mul(r.z, t0)), fp.add(fp.mul(r.w, u1), fp.mul(r.x, t2))), q.translation.y);
+				out[2].z = fp.add(fp.add(fp.sub(fp.mul(r.w, t2), fp.mul(r.x, u1)), fp.sub(fp.mul(r.z, t3), fp.mul(r.y, t0))), q.translation.z);
+			}
 		}
 
 		__device__ __forceinline__ float max_ss(float a, float b) { return a > b ? a : b; }		// _mm_max_ss: the second operand when unordered
 
-		// qvvf_transform_error_metric::calculate_error, transform_error_metrics.h:335-358 (shell points of construct_sphere_shell :261-266)
-		__device__ __forceinline__ float calculate_error(const Qvv& raw, const Qvv& lossy, float shell_distance)
+		// qvvf_transform_error_metric::calculate_error, transform_error_metrics.h:335-358: per shell point
+		// rtm::vector_distance3_as_scalar(raw, lossy) (vector4f.h:2260-2264: dot3 = (x2 + y2) + z2, :1899-1906; sqrtss), then the largest
+		__device__ __forceinline__ float calculate_error(const Fp<float2>& fp, const Qvv<float2>& object, float shell_distance)
 		{
+			Vec3<float2> points[3];
+			shell_points(fp, object, shell_distance, points);
 			float error = 0.0f;
 			#pragma unroll
 			for (int axis = 0; axis < 3; ++axis)
 			{
-				Vec3 point;
-				point.x = axis == 0 ? shell_distance : 0.0f;
-				point.y = axis == 1 ? shell_distance : 0.0f;
-				point.z = axis == 2 ? shell_distance : 0.0f;
-				const float axis_error = distance3(qvv_mul_point3(point, raw), qvv_mul_point3(point, lossy));
+				const float dx = __fsub_rn(points[axis].x.x, points[axis].x.y);
+				const float dy = __fsub_rn(points[axis].y.x, points[axis].y.y);
+				const float dz = __fsub_rn(points[axis].z.x, points[axis].z.y);
+				const float axis_error = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
 				error = axis == 0 ? axis_error : max_ss(error, axis_error);
 			}
 			return error;
 		}
 
-		__device__ __forceinline__ Qvv load_qvv48(const uint8_t* bone)
+		struct Bone48 { float4 rotation, translation, scale; };
+
+		__device__ __forceinline__ Bone48 load_bone48(const uint8_t* bone)
 		{
-			const float4 r = __ldg(reinterpret_cast<const float4*>(bone));
-			const float4 t = __ldg(reinterpret_cast<const float4*>(bone + 16));
-			const float4 s = __ldg(reinterpret_cast<const float4*>(bone + 32));
-			Qvv out;
-			out.rotation = Quat{ r.x, r.y, r.z, r.w };
-			out.translation = Vec3{ t.x, t.y, t.z };
-			out.scale = Vec3{ s.x, s.y, s.z };
+			Bone48 out;
+			out.rotation = __ldg(reinterpret_cast<const float4*>(bone));
+			out.translation = __ldg(reinterpret_cast<const float4*>(bone + 16));
+			out.scale = __ldg(reinterpret_cast<const float4*>(bone + 32));
 			return out;
 		}
 
-		__device__ __forceinline__ void store_planes(float* planes, uint32_t plane_stride, uint32_t bone, const Qvv& q)
+		__device__ __forceinline__ Qvv<float> make_qvv(const Bone48& a)
+		{
+			Qvv<float> q;
+			q.rotation = Quat<float>{ a.rotation.x, a.rotation.y, a.rotation.z, a.rotation.w };
+			q.translation = Vec3<float>{ a.translation.x, a.translation.y, a.translation.z };
+			q.scale = Vec3<float>{ a.scale.x, a.scale.y, a.scale.z };
+			return q;
+		}
+
+		__device__ __forceinline__ Qvv<float2> make_qvv(const Bone48& a, const Bone48& b)
+		{
+			Qvv<float2> q;
+			q.rotation = Quat<float2>{ make_float2(a.rotation.x, b.rotation.x), make_float2(a.rotation.y, b.rotation.y), make_float2(a.rotation.z, b.rotation.z), make_float2(a.rotation.w, b.rotation.w) };
+			q.translation = Vec3<float2>{ make_float2(a.translation.x, b.translation.x), make_float2(a.translation.y, b.translation.y), make_float2(a.translation.z, b.translation.z) };
+			q.scale = Vec3<float2>{ make_float2(a.scale.x, b.scale.x), make_float2(a.scale.y, b.scale.y), make_float2(a.scale.z, b.scale.z) };
+			return q;
+		}
+
+		// object transforms of a warp's pose in shared memory: [component][bone] planes of V (32 lanes reading 32 different parents hit
+		// different banks; a float2 plane element is one 8 byte access)
+		template<class V>
+		__device__ __forceinline__ void store_planes(V* planes, uint32_t plane_stride, uint32_t bone, const Qvv<V>& q)
 		{
 			planes[0 * plane_stride + bone] = q.rotation.x;
 			planes[1 * plane_stride + bone] = q.rotation.y;
@@ -202,9 +267,10 @@ namespace aclb200
 			planes[9 * plane_stride + bone] = q.scale.z;
 		}
 
-		__device__ __forceinline__ Qvv load_planes(const float* planes, uint32_t plane_stride, uint32_t bone)
+		template<class V>
+		__device__ __forceinline__ Qvv<V> load_planes(const V* planes, uint32_t plane_stride, uint32_t bone)
 		{
-			Qvv q;
+			Qvv<V> q;
 			q.rotation.x = planes[0 * plane_stride + bone];
 			q.rotation.y = planes[1 * plane_stride + bone];
 			q.rotation.z = planes[2 * plane_stride + bone];
@@ -267,20 +333,22 @@ namespace aclb200
 			const uint32_t* parent_indices;
 			uint32_t plane_stride;
 			uint32_t* flags;				// [1]
+			float    one;
 		};
 
 		template<int MODE>
 		__global__ void __launch_bounds__(256) object_space_kernel(ErrorParams ep, ObjectSpaceParams op)
 		{
-			extern __shared__ float object_planes[];
+			using V = typename std::conditional<MODE == 0, float2, float>::type;
+			extern __shared__ __align__(16) uint8_t object_plane_bytes[];
 			const uint32_t lane = threadIdx.x & 31u;
 			const uint32_t warp = threadIdx.x >> 5;
 			const uint32_t warps_per_block = blockDim.x >> 5;
 			const uint32_t plane_stride = MODE == 0 ? ep.plane_stride : op.plane_stride;
-			constexpr uint32_t k_streams = MODE == 0 ? 2u : 1u;
-			float* raw_planes = object_planes + size_t(warp) * k_streams * k_object_components * plane_stride;
-			float* lossy_planes = raw_planes + k_object_components * plane_stride;
+			V* planes = reinterpret_cast<V*>(object_plane_bytes) + size_t(warp) * k_object_components * plane_stride;
 			const uint64_t num_poses = MODE == 0 ? uint64_t(ep.num_poses) : op.num_poses;
+			Fp<V> fp;
+			fp.one = MODE == 0 ? ep.one : op.one;
 
 			for (uint64_t pose = uint64_t(blockIdx.x) * warps_per_block + warp; pose < num_poses; pose += uint64_t(gridDim.x) * warps_per_block)
 			{
@@ -320,69 +388,76 @@ namespace aclb200
 				{
 					const uint32_t bone = base + lane;
 					const bool active = bone < num_tracks;
-					uint32_t parent = k_invalid_track;
-					Qvv raw_local = {}, lossy_local = {};
+					// Lanes past the last bone load the last bone again (their results are never stored): no value of the loop below depends
+					// on a branch, which keeps the packed pairs in aligned register pairs from the load to the arithmetic.
+					const uint32_t load_bone = active ? bone : num_tracks - 1;
+					uint32_t parent = __ldg(parents + load_bone);
+					const Bone48 raw_local = load_bone48(raw_pose + size_t(load_bone) * 48);
 					float shell = 0.0f;
-					if (active)
+					Qvv<V> local;						// the bone's local transform (MODE 0: raw and lossy as one packed value)
+					if constexpr (MODE == 0)
 					{
-						parent = __ldg(parents + bone);
-						raw_local = load_qvv48(raw_pose + size_t(bone) * 48);
-						if (MODE == 0)
-						{
-							shell = __ldg(shells + bone);
-							// remap_output (track_error.impl.h:522-532): the raw value stands in for a bone the compressed clip does not output
-							const uint32_t output_index = output_indices != nullptr ? __ldg(output_indices + bone) : bone;
-							lossy_local = output_index != k_invalid_track ? load_qvv48(lossy_pose + size_t(output_index) * 48) : raw_local;
-						}
-						if (parent != k_invalid_track && parent >= bone)
-						{
-							// the reference would read an object transform it has not written yet: reported, the bone is treated as a root
-							pose_flags |= ACLB200_ERROR_FLAG_INVALID_SKELETON;
-							parent = k_invalid_track;
-						}
+						shell = __ldg(shells + load_bone);
+						// remap_output (track_error.impl.h:522-532): the raw value stands in for a bone the compressed clip does not output
+						const uint32_t output_index = output_indices != nullptr ? __ldg(output_indices + load_bone) : load_bone;
+						const uint8_t* lossy_bone = output_index != k_invalid_track ? lossy_pose + size_t(output_index) * 48 : raw_pose + size_t(load_bone) * 48;
+						local = make_qvv(raw_local, load_bone48(lossy_bone));
+					}
+					else
+						local = make_qvv(raw_local);
+					if (active && parent != k_invalid_track && parent >= bone)
+					{
+						// the reference would read an object transform it has not written yet: reported, the bone is treated as a root
+						pose_flags |= ACLB200_ERROR_FLAG_INVALID_SKELETON;
+						parent = k_invalid_track;
 					}
 
-					bool pending = active;
-					uint32_t done_mask = 0;				// bones of this chunk whose object transforms are in shared memory
+					// The hierarchy walk of the chunk, in wavefronts: a lane computes once its parent's object transform is in shared memory.
+					// Object transforms go straight to shared memory and come back from there for the measurement: a packed value that lives
+					// in registers across the divergent loop gets split into its halves and re-paired with moves (a third of the instructions
+					// of the first version of this kernel).
+					bool pending = active && parent != k_invalid_track;
+					if (active && parent == k_invalid_track)
+						store_planes(planes, plane_stride, bone, local);			// a root: its object transform is its local transform (:300-301)
+					__syncwarp();
+					uint32_t done_mask = __ballot_sync(0xFFFFFFFFu, active && !pending);
 					while (__any_sync(0xFFFFFFFFu, pending))
 					{
-						const bool ready = pending && (parent == k_invalid_track || parent < base || ((done_mask >> (parent - base)) & 1u) != 0);
+						const bool ready = pending && (parent < base || ((done_mask >> (parent - base)) & 1u) != 0);
 						if (ready)
 						{
-							Qvv raw_object = raw_local, lossy_object = lossy_local;
-							if (parent != k_invalid_track)
-							{
-								bool negative_raw = false, negative_lossy = false;
-								raw_object = qvv_mul_normalize(raw_local, load_planes(raw_planes, plane_stride, parent), negative_raw);
-								if (MODE == 0)
-									lossy_object = qvv_mul_normalize(lossy_local, load_planes(lossy_planes, plane_stride, parent), negative_lossy);
-								if (negative_raw || negative_lossy)
-									pose_flags |= ACLB200_ERROR_FLAG_NEGATIVE_SCALE;
-							}
-							store_planes(raw_planes, plane_stride, bone, raw_object);
-							if (MODE == 0)
-							{
-								store_planes(lossy_planes, plane_stride, bone, lossy_object);
-								const float error = calculate_error(raw_object, lossy_object, shell);
-								if (error_row != nullptr)
-									error_row[bone] = error;
-								if (error > best_error)
-								{
-									best_error = error;
-									best_bone = bone;
-								}
-							}
-							else
-							{
-								float4* out = reinterpret_cast<float4*>(op.object_poses + pose * op.pose_stride + size_t(bone) * 48);
-								out[0] = make_float4(raw_object.rotation.x, raw_object.rotation.y, raw_object.rotation.z, raw_object.rotation.w);
-								out[1] = make_float4(raw_object.translation.x, raw_object.translation.y, raw_object.translation.z, 0.0f);
-								out[2] = make_float4(raw_object.scale.x, raw_object.scale.y, raw_object.scale.z, 0.0f);
-							}
+							bool negative = false;
+							store_planes(planes, plane_stride, bone, qvv_mul_normalize(fp, local, load_planes(planes, plane_stride, parent), negative));
+							if (negative)
+								pose_flags |= ACLB200_ERROR_FLAG_NEGATIVE_SCALE;
 							pending = false;
 						}
 						__syncwarp();
 						done_mask |= __ballot_sync(0xFFFFFFFFu, ready);
+					}
+
+					// every lane of the chunk at once: the measurement (or the store) needs nothing but the lane's own object transform
+					if (active)
+					{
+						const Qvv<V> object = load_planes(planes, plane_stride, bone);
+						if constexpr (MODE == 0)
+						{
+							const float error = calculate_error(fp, object, shell);
+							if (error_row != nullptr)
+								error_row[bone] = error;
+							if (error > best_error)
+							{
+								best_error = error;
+								best_bone = bone;
+							}
+						}
+						else
+						{
+							float4* out = reinterpret_cast<float4*>(op.object_poses + pose * op.pose_stride + size_t(bone) * 48);
+							out[0] = make_float4(object.rotation.x, object.rotation.y, object.rotation.z, object.rotation.w);
+							out[1] = make_float4(object.translation.x, object.translation.y, object.translation.z, 0.0f);
+							out[2] = make_float4(object.scale.x, object.scale.y, object.scale.z, 0.0f);
+						}
 					}
 				}
 				__syncwarp();		// the next pose overwrites the planes
@@ -435,7 +510,7 @@ namespace aclb200
 			const float* lossy = reinterpret_cast<const float*>(p.lossy_poses + pose * p.pose_stride) + size_t(track) * p.components;
 			float e[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
 			for (uint32_t c = 0; c < p.components; ++c)
-				e[c] = fabsf(sub(__ldg(raw + c), __ldg(lossy + c)));
+				e[c] = fabsf(__fsub_rn(__ldg(raw + c), __ldg(lossy + c)));
 			// vector_get_max_component (external/rtm/includes/rtm/impl/vector_common.h:508-523): max(max(x, z), max(y, w)); float1f broadcasts x
 			const float error = p.components == 1 ? e[0] : max_ss(max_ss(e[0], e[2]), max_ss(e[1], e[3]));
 			if (p.error_matrix != nullptr)
@@ -542,6 +617,7 @@ extern "C"
 		op.parent_indices = d_parent_indices;
 		op.plane_stride = plane_stride_for(num_tracks);
 		op.flags = d_out_flags;
+		op.one = 1.0f;
 		const uint32_t warps = warps_for(op.plane_stride, 1, context->max_dynamic_smem);
 		if (warps == 0)
 			return set_error(context, ACLB200_ERR_UNSUPPORTED, "local_to_object_space: the skeleton's object transforms do not fit in shared memory");
@@ -726,6 +802,7 @@ extern "C"
 			p.error_stride = uint32_t(stride / bone_stride);		// tracks a pose row holds: every job fits (checked above)
 			p.plane_stride = plane_stride;
 			p.components = components;
+			p.one = 1.0f;
 
 			build_error_requests_kernel<<<(chunk.num_poses + 255) / 256, 256, 0, cuda_stream>>>(p);
 			error = cudaGetLastError();
