@@ -30,7 +30,9 @@ SEEK_STATE_DTYPE = np.dtype([
 
 # numpy views of aclb200_error_job / aclb200_track_error
 ERROR_JOB_DTYPE = np.dtype([("clip", np.uint32), ("num_samples", np.uint32), ("sample_rate", np.float32), ("duration", np.float32),
-                            ("num_tracks", np.uint32), ("skeleton_offset", np.uint32), ("first_raw_pose", np.uint64)])
+                            ("num_tracks", np.uint32), ("skeleton_offset", np.uint32), ("first_raw_pose", np.uint64),
+                            ("additive_format", np.uint32), ("reserved", np.uint32), ("first_base_pose", np.uint64)])
+ADDITIVE_NONE, ADDITIVE_RELATIVE, ADDITIVE_ADDITIVE0, ADDITIVE_ADDITIVE1 = 0, 1, 2, 3
 TRACK_ERROR_DTYPE = np.dtype([("index", np.uint32), ("error", np.float32), ("sample_time", np.float32), ("flags", np.uint32)])
 ERROR_FLAG_NEGATIVE_SCALE, ERROR_FLAG_INVALID_SKELETON = 1, 2
 
@@ -126,7 +128,7 @@ def _lib():
         l.aclb200_device_free.restype = None
         l.aclb200_copy_to_device.argtypes = [vp, vp, vp, C.c_size_t]
         l.aclb200_copy_to_host.argtypes = [vp, vp, vp, C.c_size_t]
-        l.aclb200_calculate_compression_error.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, C.POINTER(Options), vp, vp, vp]
+        l.aclb200_calculate_compression_error.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp, C.POINTER(Options), vp, vp, vp]
         l.aclb200_set_error_chunk_bytes.argtypes = [vp, u64]
         l.aclb200_local_to_object_space.argtypes = [vp, vp, vp, u64, u32, u64, vp, vp, vp]
         l.aclb200_launch_count.argtypes = [vp]
@@ -291,12 +293,13 @@ class Context:
 
     # ---- compression error measurement and the object space walk, poses stay on the device ----
     def calculate_compression_error(self, clipset: ClipSet, jobs: np.ndarray, d_raw_poses, d_parent_indices, d_shell_distances,
-                                    options: Options, d_out_errors, d_output_indices=None, d_out_error_matrix=None, stream=None) -> None:
+                                    options: Options, d_out_errors, d_output_indices=None, d_out_error_matrix=None, d_base_poses=None,
+                                    stream=None) -> None:
         jobs = np.ascontiguousarray(jobs)
         assert jobs.dtype == ERROR_JOB_DTYPE
         self._check(_lib().aclb200_calculate_compression_error(
             self._handle, clipset._handle, jobs.ctypes.data, jobs.shape[0], _device_ptr(d_raw_poses), _device_ptr(d_parent_indices),
-            _device_ptr(d_shell_distances), _device_ptr(d_output_indices), C.byref(options), _device_ptr(d_out_errors),
+            _device_ptr(d_shell_distances), _device_ptr(d_output_indices), _device_ptr(d_base_poses), C.byref(options), _device_ptr(d_out_errors),
             _device_ptr(d_out_error_matrix), _stream_ptr(stream)))
 
     def set_error_chunk_bytes(self, num_bytes: int) -> None:

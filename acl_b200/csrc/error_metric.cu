@@ -44,8 +44,11 @@ namespace aclb200
 			uint32_t job_index;				// slot of the result (the caller's job order)
 			uint64_t first_raw_pose;
 			uint64_t out_pose_base;			// first row of the job in the optional per bone error matrix
+			uint64_t first_base_pose;		// additive base: pose index of sample 0 in the base poses
+			uint32_t additive_format;		// acl::additive_clip_format8 (0 = the clip is not additive)
+			uint32_t pad;
 		};
-		static_assert(sizeof(ErrorJobDev) == 48, "ErrorJobDev is 48 bytes");
+		static_assert(sizeof(ErrorJobDev) == 64, "ErrorJobDev is 64 bytes");
 
 		struct ErrorParams
 		{
@@ -56,6 +59,7 @@ namespace aclb200
 			uint32_t* pose_jobs;			// [num_poses] index into `jobs`
 			const uint8_t* raw_poses;
 			const uint8_t* lossy_poses;		// chunk scratch, pose p at p * pose_stride
+			const uint8_t* base_poses;		// additive base poses, or nullptr
 			uint64_t pose_stride;
 			const uint32_t* parent_indices;
 			const float* shell_distances;
@@ -145,25 +149,63 @@ namespace aclb200
 			return out;
 		}
 
-		// rtm::qvv_normalize(rtm::qvv_mul(local, parent_object)), external/rtm/includes/rtm/qvvf.h:315-355,426-430, positive scale branch.
-		// `negative` reports the case the reference sends through matrices (any min(lhs.scale, rhs.scale) component < 0).
+		// rtm::qvv_mul(lhs, rhs), external/rtm/includes/rtm/qvvf.h:315-355, positive scale branch. `negative` reports the case the reference
+		// sends through matrices (any min(lhs.scale, rhs.scale) component < 0).
+		template<class V>
+		__device__ __forceinline__ Qvv<V> qvv_mul(const Fp<V>& fp, const Qvv<V>& lhs, const Qvv<V>& rhs, bool& negative)
+		{
+			negative = fp.any_negative(lhs.scale.x, rhs.scale.x) || fp.any_negative(lhs.scale.y, rhs.scale.y) || fp.any_negative(lhs.scale.z, rhs.scale.z);
+			Qvv<V> out;
+			out.rotation = quat_mul(fp, lhs.rotation, rhs.rotation);
+			Vec3<V> scaled;
+			scaled.x = fp.mul(lhs.translation.x, rhs.scale.x);
+			scaled.y = fp.mul(lhs.translation.y, rhs.scale.y);
+			scaled.z = fp.mul(lhs.translation.z, rhs.scale.z);
+			const Vec3<V> rotated = quat_mul_vector3(fp, scaled, rhs.rotation);
+			out.translation.x = fp.add(rotated.x, rhs.translation.x);
+			out.translation.y = fp.add(rotated.y, rhs.translation.y);
+			out.translation.z = fp.add(rotated.z, rhs.translation.z);
+			out.scale.x = fp.mul(lhs.scale.x, rhs.scale.x);
+			out.scale.y = fp.mul(lhs.scale.y, rhs.scale.y);
+			out.scale.z = fp.mul(lhs.scale.z, rhs.scale.z);
+			return out;
+		}
+
+		// rtm::qvv_normalize(rtm::qvv_mul(local, parent_object)), qvvf.h:426-430: what local_to_object_space does per bone
 		template<class V>
 		__device__ __forceinline__ Qvv<V> qvv_mul_normalize(const Fp<V>& fp, const Qvv<V>& local, const Qvv<V>& parent, bool& negative)
 		{
-			negative = fp.any_negative(local.scale.x, parent.scale.x) || fp.any_negative(local.scale.y, parent.scale.y) || fp.any_negative(local.scale.z, parent.scale.z);
+			Qvv<V> out = qvv_mul(fp, local, parent, negative);
+			out.rotation = quat_normalize(fp, out.rotation);
+			return out;
+		}
+
+		// acl::apply_additive_to_base(format, base, additive), includes/acl/core/additive_utils.h:131-167 (format = additive_clip_format8:
+		// 1 relative, 2 additive0, 3 additive1; transform_add0 / transform_add1 :131-145)
+		template<class V>
+		__device__ __forceinline__ Qvv<V> apply_additive_to_base(const Fp<V>& fp, uint32_t format, const Qvv<V>& base, const Qvv<V>& additive, bool& negative)
+		{
+			negative = false;
+			if (format == 1)
+				return qvv_mul(fp, additive, base, negative);
 			Qvv<V> out;
-			out.rotation = quat_normalize(fp, quat_mul(fp, local.rotation, parent.rotation));
-			Vec3<V> scaled;
-			scaled.x = fp.mul(local.translation.x, parent.scale.x);
-			scaled.y = fp.mul(local.translation.y, parent.scale.y);
-			scaled.z = fp.mul(local.translation.z, parent.scale.z);
-			const Vec3<V> rotated = quat_mul_vector3(fp, scaled, parent.rotation);
-			out.translation.x = fp.add(rotated.x, parent.translation.x);
-			out.translation.y = fp.add(rotated.y, parent.translation.y);
-			out.translation.z = fp.add(rotated.z, parent.translation.z);
-			out.scale.x = fp.mul(local.scale.x, parent.scale.x);
-			out.scale.y = fp.mul(local.scale.y, parent.scale.y);
-			out.scale.z = fp.mul(local.scale.z, parent.scale.z);
+			out.rotation = quat_mul(fp, additive.rotation, base.rotation);
+			out.translation.x = fp.add(additive.translation.x, base.translation.x);
+			out.translation.y = fp.add(additive.translation.y, base.translation.y);
+			out.translation.z = fp.add(additive.translation.z, base.translation.z);
+			if (format == 2)
+			{
+				out.scale.x = fp.mul(additive.scale.x, base.scale.x);
+				out.scale.y = fp.mul(additive.scale.y, base.scale.y);
+				out.scale.z = fp.mul(additive.scale.z, base.scale.z);
+			}
+			else
+			{
+				const V one = fp.splat(1.0f);
+				out.scale.x = fp.mul(fp.add(one, additive.scale.x), base.scale.x);
+				out.scale.y = fp.mul(fp.add(one, additive.scale.y), base.scale.y);
+				out.scale.z = fp.mul(fp.add(one, additive.scale.z), base.scale.z);
+			}
 			return out;
 		}
 
@@ -359,9 +401,16 @@ namespace aclb200
 				const float* shells = nullptr;
 				const uint32_t* output_indices = nullptr;
 				float* error_row = nullptr;
+				const uint8_t* base_pose = nullptr;
+				uint32_t additive_format = 0;
 				if (MODE == 0)
 				{
 					const ErrorJobDev job = ep.jobs[ep.pose_jobs[pose]];
+					if (ep.base_poses != nullptr && job.additive_format != 0)
+					{
+						additive_format = job.additive_format;
+						base_pose = ep.base_poses + (job.first_base_pose + (uint32_t(pose) - job.chunk_first_pose)) * ep.pose_stride;
+					}
 					num_tracks = job.num_tracks;
 					sample = uint32_t(pose) - job.chunk_first_pose;
 					job_slot = job.job_index;
@@ -402,6 +451,15 @@ namespace aclb200
 						const uint32_t output_index = output_indices != nullptr ? __ldg(output_indices + load_bone) : load_bone;
 						const uint8_t* lossy_bone = output_index != k_invalid_track ? lossy_pose + size_t(output_index) * 48 : raw_pose + size_t(load_bone) * 48;
 						local = make_qvv(raw_local, load_bone48(lossy_bone));
+						if (additive_format != 0)
+						{
+							// apply_additive_to_base on the raw and on the lossy pose before the walk (track_error.impl.h:358-359)
+							const Bone48 base = load_bone48(base_pose + size_t(load_bone) * 48);
+							bool negative = false;
+							local = apply_additive_to_base(fp, additive_format, make_qvv(base, base), local, negative);
+							if (negative && active)
+								pose_flags |= ACLB200_ERROR_FLAG_NEGATIVE_SCALE;
+						}
 					}
 					else
 						local = make_qvv(raw_local);
@@ -642,7 +700,8 @@ extern "C"
 
 	aclb200_status aclb200_calculate_compression_error(aclb200_context* context, const aclb200_clipset* clipset, const aclb200_error_job* jobs,
 		uint32_t num_jobs, const void* d_raw_poses, const uint32_t* d_parent_indices, const float* d_shell_distances,
-		const uint32_t* d_output_indices, const aclb200_options* options, aclb200_track_error* d_out_errors, float* d_out_error_matrix, void* stream)
+		const uint32_t* d_output_indices, const void* d_base_poses, const aclb200_options* options, aclb200_track_error* d_out_errors,
+		float* d_out_error_matrix, void* stream)
 	{
 		if (context == nullptr || clipset == nullptr || options == nullptr)
 			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "null context / clipset / options");
@@ -667,7 +726,7 @@ extern "C"
 		const uint32_t bone_stride = is_transform ? 48u : components * 4u;
 		const uint64_t stride = options->pose_stride_bytes != 0 ? options->pose_stride_bytes : uint64_t(clipset->info.max_tracks) * bone_stride;
 		const uint64_t alignment = is_transform ? 16 : 4;
-		if ((stride % alignment) != 0 || (reinterpret_cast<uintptr_t>(d_raw_poses) % alignment) != 0)
+		if ((stride % alignment) != 0 || (reinterpret_cast<uintptr_t>(d_raw_poses) % alignment) != 0 || (reinterpret_cast<uintptr_t>(d_base_poses) % alignment) != 0)
 			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "calculate_compression_error: raw poses must be 16 byte aligned rtm::qvvf rows (4 byte aligned scalar rows)");
 
 		// jobs in processing order: the clips sought with `nearest`, then the ones sought with `none` (stripped key frames leave holes
@@ -686,6 +745,8 @@ extern "C"
 				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "calculate_compression_error: job has more tracks than a pose row holds");
 			if (d_output_indices == nullptr && job.num_tracks != clipset->host_clips[job.clip].num_tracks)
 				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "calculate_compression_error: raw and compressed track counts differ (pass output indices)");
+			if (job.additive_format > 3 || (job.additive_format != 0 && (d_base_poses == nullptr || !is_transform)))
+				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "calculate_compression_error: additive format out of range, or an additive job without base poses");
 			if (uint64_t(job.num_samples) * std::max(job.num_tracks, 1u) > 0xFFFFFFFFull)
 				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "calculate_compression_error: samples x tracks of a job must fit 32 bits");
 			out_base[index] = total_poses;
@@ -710,6 +771,8 @@ extern "C"
 				dev.duration = job.duration;
 				dev.job_index = index;
 				dev.first_raw_pose = job.first_raw_pose;
+				dev.first_base_pose = job.first_base_pose;
+				dev.additive_format = job.additive_format;
 				dev.out_pose_base = out_base[index];
 				ordered.push_back(dev);
 			}
@@ -792,6 +855,7 @@ extern "C"
 			p.pose_jobs = d_pose_jobs;
 			p.raw_poses = static_cast<const uint8_t*>(d_raw_poses);
 			p.lossy_poses = d_lossy;
+			p.base_poses = static_cast<const uint8_t*>(d_base_poses);
 			p.pose_stride = stride;
 			p.parent_indices = d_parent_indices;
 			p.shell_distances = d_shell_distances;

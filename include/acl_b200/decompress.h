@@ -543,6 +543,9 @@ namespace acl_b200
 		}
 		const compressed_tracks* get_compressed_tracks() const { return m_bound; }
 		bool is_initialized() const { return m_bound != nullptr; }
+		// the device side of the bound clip (a clip set of one), for the callers of the decode that run on the device as well
+		// (acl_b200/track_error.h)
+		batch_decompressor& device_batch() { return batch(); }
 		// is_bound_to_v0, decompression.transform.h:159-176: same address and same hash
 		bool is_bound_to(const compressed_tracks& tracks) const { return m_bound == &tracks && m_hash == tracks.get_hash(); }
 		void set_looping_policy(sample_looping_policy policy)

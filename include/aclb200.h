@@ -266,6 +266,9 @@ typedef struct aclb200_error_job
 	uint32_t num_tracks;			/* raw_tracks.get_num_tracks() */
 	uint32_t skeleton_offset;		/* first entry of this clip's skeleton in d_parent_indices / d_shell_distances / d_output_indices */
 	uint64_t first_raw_pose;		/* pose index of sample 0 in d_raw_poses */
+	uint32_t additive_format;		/* acl::additive_clip_format8 (core/additive_utils.h:42-66): 0 none, 1 relative, 2 additive0, 3 additive1 */
+	uint32_t reserved;				/* 0 */
+	uint64_t first_base_pose;		/* additive jobs: pose index of sample 0 in d_base_poses */
 } aclb200_error_job;
 
 /* Replaces calculate_compression_error (compression/impl/track_error.impl.h:400-571: calculate_transform_track_error :225-392 with the
@@ -279,14 +282,20 @@ typedef struct aclb200_error_job
  *   d_shell_distances device: track_desc_transformf::shell_distance per track; both unused (NULL) for scalar clip sets
  *   d_output_indices  device, optional: track_desc::output_index per raw track (0xFFFFFFFF = stripped from the compressed clip: the raw
  *                     value stands in, track_error.impl.h:522-532); NULL = every raw track i is output i
+ *   d_base_poses      device, optional: the additive base of the jobs whose additive_format is not 0 (the calculate_compression_error
+ *                     overload with additive_base_tracks, track_error.impl.h:573-680, + additive_qvvf_transform_error_metric<format>,
+ *                     transform_error_metrics.h:470-526): pose s of a job is `additive_base_tracks.sample_tracks(t_base(s), rounding, writer)`
+ *                     with t_base = (t / duration) * base_duration, or 0 when the base has one sample (:352-356); it is applied to the raw
+ *                     and to the decoded pose with acl::apply_additive_to_base (core/additive_utils.h:147-157) before the hierarchy walk
  *   d_out_errors      device: one aclb200_track_error per job
  *   d_out_error_matrix device, optional: the error of every bone of every pose, row (poses of the earlier jobs + s) of
  *                     pose_stride_bytes / 48 floats (= max_tracks by default; scalar clip sets: tracks per row)
- * No additive base (track_error.impl.h:573-680). rtm::quat_normalize's rsqrtss estimate is CPU specific: errors agree with a given CPU's
+ * rtm::quat_normalize's rsqrtss estimate is CPU specific: errors agree with a given CPU's
  * within 5e-5 on poses tens of units across, not bit for bit (see error_metric.cu). Asynchronous on `stream`; uses scratch owned by the context. */
 ACLB200_API aclb200_status aclb200_calculate_compression_error(aclb200_context* context, const aclb200_clipset* clipset, const aclb200_error_job* jobs,
 	uint32_t num_jobs, const void* d_raw_poses, const uint32_t* d_parent_indices, const float* d_shell_distances,
-	const uint32_t* d_output_indices, const aclb200_options* options, aclb200_track_error* d_out_errors, float* d_out_error_matrix, void* stream);
+	const uint32_t* d_output_indices, const void* d_base_poses, const aclb200_options* options, aclb200_track_error* d_out_errors,
+	float* d_out_error_matrix, void* stream);
 
 /* Decoded poses held per chunk of clips by aclb200_calculate_compression_error (default 512 MiB). */
 ACLB200_API aclb200_status aclb200_set_error_chunk_bytes(aclb200_context* context, uint64_t bytes);

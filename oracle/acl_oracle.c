@@ -1437,6 +1437,62 @@ static int qvv_mul_normalize(const float local[12], const float parent[12], int 
 	return negative;
 }
 
+/* rtm::qvv_mul(lhs, rhs), qvvf.h:315-355, positive scale branch, no normalisation. Returns 1 for the negative scale branch. */
+static int qvv_mul_plain(const float lhs[12], const float rhs[12], float out[12])
+{
+	int negative = 0;
+	for (int i = 0; i < 3; ++i)
+	{
+		const float min_scale = lhs[8 + i] < rhs[8 + i] ? lhs[8 + i] : rhs[8 + i];
+		negative |= min_scale < 0.0f;
+	}
+	float rotation[4];
+	rtm_quat_mul(lhs + 0, rhs + 0, rotation);
+	const float scaled[3] = { lhs[4] * rhs[8], lhs[5] * rhs[9], lhs[6] * rhs[10] };
+	float rotated[3];
+	rtm_quat_mul_vector3(scaled, rhs + 0, rotated);
+	float result[12];
+	for (int i = 0; i < 4; ++i)
+		result[i] = rotation[i];
+	for (int i = 0; i < 3; ++i)
+	{
+		result[4 + i] = rotated[i] + rhs[4 + i];
+		result[8 + i] = lhs[8 + i] * rhs[8 + i];
+	}
+	result[7] = 0.0f;
+	result[11] = 0.0f;
+	memcpy(out, result, sizeof(result));
+	return negative;
+}
+
+/* acl::apply_additive_to_base(format, base, additive), core/additive_utils.h:131-167, over a pose, in place on `pose` (the additive one):
+ * 0 none, 1 relative = qvv_mul(additive, base), 2 additive0 (scale = additive * base), 3 additive1 (scale = (1 + additive) * base).
+ * Returns 1 when `relative` met a negative scale. */
+int aclo_apply_additive_to_base(uint32_t additive_format, const float* base_pose, float* pose, uint32_t num_tracks)
+{
+	int negative = 0;
+	for (uint32_t bone = 0; bone < num_tracks; ++bone)
+	{
+		const float* base = base_pose + (size_t)bone * 12;
+		float* additive = pose + (size_t)bone * 12;
+		if (additive_format == 1)
+			negative |= qvv_mul_plain(additive, base, additive);
+		else if (additive_format == 2 || additive_format == 3)
+		{
+			float rotation[4];
+			rtm_quat_mul(additive + 0, base + 0, rotation);
+			for (int i = 0; i < 4; ++i)
+				additive[i] = rotation[i];
+			for (int i = 0; i < 3; ++i)
+			{
+				additive[4 + i] = additive[4 + i] + base[4 + i];
+				additive[8 + i] = additive_format == 2 ? additive[8 + i] * base[8 + i] : (1.0f + additive[8 + i]) * base[8 + i];
+			}
+		}
+	}
+	return negative;
+}
+
 /* qvvf_transform_error_metric::local_to_object_space, transform_error_metrics.h:289-310 (all transforms dirty, in index order) */
 int aclo_local_to_object_space(const float* local_pose, const uint32_t* parent_indices, uint32_t num_tracks, int normalize_mode, float* out_object_pose)
 {
@@ -1491,11 +1547,13 @@ float aclo_calculate_error(const float* raw_object_bone, const float* lossy_obje
 
 /* The sample loop of calculate_transform_track_error (track_error.impl.h:225-392) once both pose streams are sampled:
  * raw_poses = raw_tracks.sample_tracks(t_i), lossy_poses = seek(t_i) + decompress_tracks (already remapped, :341), both
- * [num_samples][num_tracks][12]; t_i = min(i / sample_rate, duration) (:337). No additive base. out_errors (optional):
+ * [num_samples][num_tracks][12]; t_i = min(i / sample_rate, duration) (:337). base_poses (optional): the additive base sampled at the matching
+ * times (:352-356), applied to both poses with `additive_format` (:358-359). out_errors (optional):
  * [num_samples][num_tracks]. Returns < 0 for an invalid skeleton order, 1 if a negative scale was met (result not the reference's). */
 int aclo_transform_track_error(const float* raw_poses, const float* lossy_poses, uint32_t num_samples, uint32_t num_tracks,
 	float sample_rate, float duration, const uint32_t* parent_indices, const float* shell_distances, int normalize_mode,
-	aclo_track_error* out_error, float* out_errors, float* scratch_object_poses /* [2][num_tracks][12] */)
+	aclo_track_error* out_error, float* out_errors, float* scratch_object_poses /* [4][num_tracks][12] */,
+	const float* base_poses /* [num_samples][num_tracks][12] or NULL */, uint32_t additive_format)
 {
 	out_error->index = 0xFFFFFFFFu;		/* track_error(), track_error.h:48-62 */
 	out_error->error = 0.0f;
@@ -1512,8 +1570,22 @@ int aclo_transform_track_error(const float* raw_poses, const float* lossy_poses,
 		const float t = (float)sample / sample_rate;
 		const float sample_time = t < duration ? t : duration;		/* rtm::scalar_min */
 		const size_t pose = (size_t)sample * num_tracks * 12;
-		const int r0 = aclo_local_to_object_space(raw_poses + pose, parent_indices, num_tracks, normalize_mode, raw_object);
-		const int r1 = aclo_local_to_object_space(lossy_poses + pose, parent_indices, num_tracks, normalize_mode, lossy_object);
+		const float* raw_local = raw_poses + pose;
+		const float* lossy_local = lossy_poses + pose;
+		if (base_poses != NULL && additive_format != 0)
+		{
+			/* apply_additive_to_base on both poses before the walk (:358-359) */
+			float* raw_applied = scratch_object_poses + (size_t)num_tracks * 24;
+			float* lossy_applied = scratch_object_poses + (size_t)num_tracks * 36;
+			memcpy(raw_applied, raw_local, (size_t)num_tracks * 12 * sizeof(float));
+			memcpy(lossy_applied, lossy_local, (size_t)num_tracks * 12 * sizeof(float));
+			negative |= aclo_apply_additive_to_base(additive_format, base_poses + pose, raw_applied, num_tracks);
+			negative |= aclo_apply_additive_to_base(additive_format, base_poses + pose, lossy_applied, num_tracks);
+			raw_local = raw_applied;
+			lossy_local = lossy_applied;
+		}
+		const int r0 = aclo_local_to_object_space(raw_local, parent_indices, num_tracks, normalize_mode, raw_object);
+		const int r1 = aclo_local_to_object_space(lossy_local, parent_indices, num_tracks, normalize_mode, lossy_object);
 		if (r0 < 0 || r1 < 0)
 			return -1;
 		negative |= r0 | r1;

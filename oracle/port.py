@@ -252,7 +252,8 @@ def local_to_object_space(local_pose: np.ndarray, parents: np.ndarray, normalize
 
 
 def transform_track_error(raw_poses: np.ndarray, lossy_poses: np.ndarray, sample_rate: float, duration: float, parents: np.ndarray,
-                          shell_distances: np.ndarray, normalize_mode: int = NORMALIZE_IEEE):
+                          shell_distances: np.ndarray, normalize_mode: int = NORMALIZE_IEEE, base_poses: np.ndarray | None = None,
+                          additive_format: int = 0):
     """The loop of calculate_transform_track_error over [num_samples][num_tracks][12] poses.
     Returns (TrackError, errors float32 [num_samples][num_tracks], negative_scale_seen)."""
     raw_poses = np.ascontiguousarray(raw_poses, dtype=np.float32)
@@ -262,16 +263,30 @@ def transform_track_error(raw_poses: np.ndarray, lossy_poses: np.ndarray, sample
     num_samples, num_tracks = raw_poses.shape[0], raw_poses.shape[1]
     assert lossy_poses.shape == raw_poses.shape and raw_poses.shape[2] == 12
     errors = np.zeros((num_samples, num_tracks), dtype=np.float32)
-    scratch = np.zeros((2, max(num_tracks, 1), 12), dtype=np.float32)
+    scratch = np.zeros((4, max(num_tracks, 1), 12), dtype=np.float32)
+    if base_poses is not None:
+        base_poses = np.ascontiguousarray(base_poses, dtype=np.float32)
+        assert base_poses.shape == raw_poses.shape
     result = TrackError()
     fn = lib().aclo_transform_track_error
     fn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
-                   C.POINTER(TrackError), C.c_void_p, C.c_void_p]
+                   C.POINTER(TrackError), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
     rc = fn(raw_poses.ctypes.data, lossy_poses.ctypes.data, num_samples, num_tracks, sample_rate, duration, parents.ctypes.data,
-            shell_distances.ctypes.data, normalize_mode, C.byref(result), errors.ctypes.data, scratch.ctypes.data)
+            shell_distances.ctypes.data, normalize_mode, C.byref(result), errors.ctypes.data, scratch.ctypes.data,
+            None if base_poses is None else base_poses.ctypes.data, additive_format)
     if rc < 0:
         raise RuntimeError("aclo_transform_track_error: a parent does not precede its child")
     return result, errors, rc == 1
+
+
+def apply_additive_to_base(additive_format: int, base_pose: np.ndarray, pose: np.ndarray) -> np.ndarray:
+    """acl::apply_additive_to_base over one pose [num_tracks][12]; returns the combined pose."""
+    base_pose = np.ascontiguousarray(base_pose, dtype=np.float32)
+    out = np.array(pose, dtype=np.float32, order="C", copy=True)
+    fn = lib().aclo_apply_additive_to_base
+    fn.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
+    fn(additive_format, base_pose.ctypes.data, out.ctypes.data, out.shape[0])
+    return out
 
 
 def scalar_track_error(raw_values: np.ndarray, lossy_values: np.ndarray, components: int, sample_rate: float, duration: float) -> TrackError:

@@ -386,3 +386,27 @@ def sample_raw_transform_batch(spec: TransformSpec, num_clips: int, num_threads:
     if rc != 0:
         raise RuntimeError("aclref_sample_raw_transform_batch failed")
     return raw, parents, shells
+
+
+ADDITIVE_NONE, ADDITIVE_RELATIVE, ADDITIVE_ADDITIVE0, ADDITIVE_ADDITIVE1 = 0, 1, 2, 3     # acl::additive_clip_format8 (core/additive_utils.h:42-66)
+
+
+def transform_error_additive(spec: TransformSpec, blob: np.ndarray, base_spec: TransformSpec, additive_format: int) -> dict:
+    """calculate_compression_error(allocator, raw clip of `spec`, context(blob), additive_qvvf_transform_error_metric<format>, raw clip of
+    `base_spec`) with debug settings. As transform_error, plus base_poses float32 [num_samples][num_tracks][12] (the base clip sampled at the
+    matching times) and errors measured after apply_additive_to_base."""
+    n, m = spec.num_tracks, spec.num_samples
+    out = dict(raw_poses=np.zeros((m, n, 12), np.float32), lossy_poses=np.zeros((m, n, 12), np.float32), base_poses=np.zeros((m, n, 12), np.float32),
+               errors=np.zeros((m, n), np.float32), parents=np.zeros(n, np.uint32), shell_distances=np.zeros(n, np.float32))
+    result, rounding = TrackError(), C.c_uint32()
+    fn = lib().aclref_transform_error_additive
+    fn.argtypes = [C.POINTER(_TransformSpec), C.c_void_p, C.POINTER(_TransformSpec), C.c_uint32, C.POINTER(TrackError), C.POINTER(C.c_uint32)] + [C.c_void_p] * 6
+    c_spec, c_base = spec.to_c(), base_spec.to_c()
+    rc = fn(C.byref(c_spec), blob.ctypes.data, C.byref(c_base), additive_format, C.byref(result), C.byref(rounding), out["raw_poses"].ctypes.data,
+            out["lossy_poses"].ctypes.data, out["base_poses"].ctypes.data, out["errors"].ctypes.data, out["parents"].ctypes.data,
+            out["shell_distances"].ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"aclref_transform_error_additive failed ({rc})")
+    out.update(index=int(result.index), error=float(result.error), sample_time=float(result.sample_time), rounding=int(rounding.value),
+               sample_rate=float(spec.sample_rate), duration=finite_duration(m, spec.sample_rate), additive_format=additive_format)
+    return out

@@ -1002,6 +1002,123 @@ extern "C"
 		return transform_error_impl<settings_debug>(*spec, tracks, out_error, out_rounding, out_raw_poses, out_lossy_poses, out_object_poses, out_errors, out_parents, out_shell_distances);
 	}
 
+	// The additive flavour: calculate_compression_error(allocator, raw_tracks, context, error_metric, additive_base_tracks)
+	// (track_error.impl.h:573-680) with additive_qvvf_transform_error_metric<format> (transform_error_metrics.h:470-526). The raw clip of `spec`
+	// plays the additive clip, the raw clip of `base_spec` (same track count, any sample count) the base it applies to; `blob` is what
+	// aclref_compress_transform(spec) returned. additive_format: acl::additive_clip_format8 (1 relative, 2 additive0, 3 additive1).
+	// Outputs as aclref_transform_error, plus out_base_poses [num_samples][num_tracks][12] = additive_base_tracks.sample_tracks at the
+	// base clip's matching time (track_error.impl.h:352-356); out_errors are measured after apply_additive_to_base on both poses.
+	int aclref_transform_error_additive(const aclref_transform_spec* spec, const void* blob, const aclref_transform_spec* base_spec, uint32_t additive_format,
+		aclref_track_error* out_error, uint32_t* out_rounding, float* out_raw_poses, float* out_lossy_poses, float* out_base_poses, float* out_errors,
+		uint32_t* out_parents, float* out_shell_distances)
+	{
+		const compressed_tracks& tracks = *static_cast<const compressed_tracks*>(blob);
+		if (tracks.get_track_type() != track_type8::qvvf || tracks.get_num_tracks() != spec->num_tracks || base_spec->num_tracks != spec->num_tracks)
+			return -2;
+		iallocator& alloc = allocator();
+		track_array_qvvf raw_tracks(alloc, spec->num_tracks);
+		make_transform_tracks(*spec, raw_tracks);
+		track_array_qvvf base_tracks(alloc, base_spec->num_tracks);
+		make_transform_tracks(*base_spec, base_tracks);
+
+		decompression_context<settings_debug> context;
+		if (!context.initialize(tracks))
+			return -1;
+
+		const additive_qvvf_transform_error_metric<additive_clip_format8::relative> metric_relative;
+		const additive_qvvf_transform_error_metric<additive_clip_format8::additive0> metric_additive0;
+		const additive_qvvf_transform_error_metric<additive_clip_format8::additive1> metric_additive1;
+		const itransform_error_metric* metric = nullptr;
+		switch (static_cast<additive_clip_format8>(additive_format))
+		{
+		case additive_clip_format8::relative: metric = &metric_relative; break;
+		case additive_clip_format8::additive0: metric = &metric_additive0; break;
+		case additive_clip_format8::additive1: metric = &metric_additive1; break;
+		default: return -3;
+		}
+		const itransform_error_metric& error_metric = *metric;
+
+		const track_error result = calculate_compression_error(alloc, raw_tracks, context, error_metric, base_tracks);
+		out_error->index = result.index;
+		out_error->error = result.error;
+		out_error->sample_time = result.sample_time;
+
+		const sample_rounding_policy rounding = (tracks.has_database() || tracks.has_stripped_keyframes()) ? sample_rounding_policy::none : sample_rounding_policy::nearest;
+		if (out_rounding != nullptr)
+			*out_rounding = uint32_t(rounding);
+
+		const uint32_t num_tracks = raw_tracks.get_num_tracks();
+		const uint32_t num_samples = raw_tracks.get_num_samples_per_track();
+		const float sample_rate = raw_tracks.get_sample_rate();
+		const float duration = raw_tracks.get_finite_duration();
+		const uint32_t base_num_samples = base_tracks.get_num_samples_per_track();
+		const float base_duration = base_tracks.get_finite_duration();
+
+		std::vector<uint32_t> parents(num_tracks), self(num_tracks);
+		for (uint32_t bone = 0; bone < num_tracks; ++bone)
+		{
+			const track_desc_transformf& desc = raw_tracks[bone].get_description();
+			parents[bone] = desc.parent_index;
+			self[bone] = bone;
+			if (out_parents != nullptr) out_parents[bone] = desc.parent_index;
+			if (out_shell_distances != nullptr) out_shell_distances[bone] = desc.shell_distance;
+		}
+
+		acl_impl::debug_track_writer raw_writer(alloc, track_type8::qvvf, num_tracks);
+		acl_impl::debug_track_writer lossy_writer(alloc, track_type8::qvvf, num_tracks);
+		acl_impl::debug_track_writer base_writer(alloc, track_type8::qvvf, num_tracks);
+		lossy_writer.initialize_with_defaults(raw_tracks);
+		std::vector<rtm::qvvf> raw_object(num_tracks), lossy_object(num_tracks);
+
+		itransform_error_metric::apply_additive_to_base_args additive_args;
+		additive_args.dirty_transform_indices = self.data();
+		additive_args.num_dirty_transforms = num_tracks;
+		additive_args.base_transforms = base_writer.tracks_typed.qvvf;
+		additive_args.num_transforms = num_tracks;
+		itransform_error_metric::local_to_object_space_args object_args;
+		object_args.dirty_transform_indices = self.data();
+		object_args.num_dirty_transforms = num_tracks;
+		object_args.parent_transform_indices = parents.data();
+		object_args.num_transforms = num_tracks;
+
+		for (uint32_t sample = 0; sample < num_samples; ++sample)
+		{
+			const float sample_time = rtm::scalar_min(float(sample) / sample_rate, duration);
+			raw_tracks.sample_tracks(sample_time, rounding, raw_writer);
+			context.seek(sample_time, rounding);
+			context.decompress_tracks(lossy_writer);
+			const float normalized_sample_time = base_num_samples > 1 ? (sample_time / duration) : 0.0F;		// track_error.impl.h:352-353
+			const float additive_sample_time = base_num_samples > 1 ? (normalized_sample_time * base_duration) : 0.0F;
+			base_tracks.sample_tracks(additive_sample_time, rounding, base_writer);
+
+			const size_t pose_floats = size_t(num_tracks) * 12;
+			if (out_raw_poses != nullptr) std::memcpy(out_raw_poses + sample * pose_floats, raw_writer.tracks_typed.qvvf, pose_floats * sizeof(float));
+			if (out_lossy_poses != nullptr) std::memcpy(out_lossy_poses + sample * pose_floats, lossy_writer.tracks_typed.qvvf, pose_floats * sizeof(float));
+			if (out_base_poses != nullptr) std::memcpy(out_base_poses + sample * pose_floats, base_writer.tracks_typed.qvvf, pose_floats * sizeof(float));
+
+			std::vector<rtm::qvvf> raw_local(raw_writer.tracks_typed.qvvf, raw_writer.tracks_typed.qvvf + num_tracks);
+			std::vector<rtm::qvvf> lossy_local(lossy_writer.tracks_typed.qvvf, lossy_writer.tracks_typed.qvvf + num_tracks);
+			additive_args.local_transforms = raw_local.data();
+			error_metric.apply_additive_to_base(additive_args, raw_local.data());
+			additive_args.local_transforms = lossy_local.data();
+			error_metric.apply_additive_to_base(additive_args, lossy_local.data());
+			object_args.local_transforms = raw_local.data();
+			error_metric.local_to_object_space(object_args, raw_object.data());
+			object_args.local_transforms = lossy_local.data();
+			error_metric.local_to_object_space(object_args, lossy_object.data());
+			if (out_errors != nullptr)
+				for (uint32_t bone = 0; bone < num_tracks; ++bone)
+				{
+					itransform_error_metric::calculate_error_args error_args;
+					error_args.transform0 = &raw_object[bone];
+					error_args.transform1 = &lossy_object[bone];
+					error_args.construct_sphere_shell(raw_tracks[bone].get_description().shell_distance);
+					out_errors[size_t(sample) * num_tracks + bone] = rtm::scalar_cast(error_metric.calculate_error(error_args));
+				}
+		}
+		return 0;
+	}
+
 	// The scalar flavour: calculate_compression_error(allocator, raw_tracks, context) (track_error.impl.h:400-463 -> calculate_scalar_track_error
 	// :166-223). out_raw_values [num_samples][num_tracks][4] = raw_tracks.sample_tracks(...) (first N components of each row).
 	int aclref_scalar_error(const aclref_scalar_spec* spec, const void* blob, aclref_track_error* out_error, uint32_t* out_rounding, float* out_raw_values)

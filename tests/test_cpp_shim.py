@@ -93,14 +93,18 @@ REFERENCE_INCLUDES = ["/root/reference/includes", "/root/reference/external/rtm/
 CALLSITE_EXE = os.path.join(ROOT, "tests", "cpp", "_build", "shim_reference_callsite")
 
 
+TRACK_ERROR_EXE = os.path.join(ROOT, "tests", "cpp", "_build", "shim_track_error")
+
+
 def build_reference_callsite():
-    """tests/cpp/shim_reference_callsite.cpp needs the reference's headers: it is built where /root/reference exists
-    (__graft_entry__.build() does it too) and travels to the GPU box prebuilt, like oracle/_ref."""
+    """tests/cpp/shim_reference_callsite.cpp and shim_track_error.cpp need the reference's headers: they are built where /root/reference
+    exists (__graft_entry__.build() does it too) and travel to the GPU box prebuilt, like oracle/_ref."""
     os.makedirs(os.path.dirname(CALLSITE_EXE), exist_ok=True)
-    cmd = ["g++", "-std=c++14", "-O2", "-msse4.1", "-ffp-contract=off", "-Wall", "-Wextra"] + ["-I" + d for d in REFERENCE_INCLUDES] + [
-        "-o", CALLSITE_EXE, os.path.join(ROOT, "tests", "cpp", "shim_reference_callsite.cpp"),
-        "-L" + os.path.join(ROOT, "acl_b200"), "-laclb200", "-Wl,-rpath,$ORIGIN/../../../acl_b200"]
-    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    for exe in (CALLSITE_EXE, TRACK_ERROR_EXE):
+        cmd = ["g++", "-std=c++14", "-O2", "-msse4.1", "-ffp-contract=off", "-Wall", "-Wextra", "-Werror"] + ["-I" + d for d in REFERENCE_INCLUDES] + [
+            "-o", exe, os.path.join(ROOT, "tests", "cpp", os.path.basename(exe) + ".cpp"),
+            "-L" + os.path.join(ROOT, "acl_b200"), "-laclb200", "-Wl,-rpath,$ORIGIN/../../../acl_b200"]
+        subprocess.run(cmd, check=True, capture_output=True, text=True)
 
 
 @pytest.mark.skipif(not all(os.path.isdir(d) for d in REFERENCE_INCLUDES), reason="needs the reference's headers")
@@ -137,4 +141,27 @@ def test_binding_semantics_follow_the_reference(tmp_path):
     exe = build_shim_program(tmp_path, "shim_binding")
     golden = os.path.join(ROOT, "tests", "golden")
     result = subprocess.run([exe, os.path.join(golden, "c1_30bones.acl.bin"), os.path.join(golden, "mixed_scale.acl.bin")], capture_output=True, text=True)
+    assert result.returncode == 0 and "PASS" in result.stdout, (result.stdout, result.stderr)
+
+
+@pytest.mark.skipif(not all(os.path.isdir(d) for d in REFERENCE_INCLUDES), reason="needs the reference's headers")
+def test_track_error_callsite_compiles_against_the_shim():
+    """acl_b200/track_error.h: calculate_compression_error(allocator, raw_tracks, context[, error_metric]) with the reference's signature
+    and types (compression/track_error.h:64-91). Without a GPU the program must stop with NO_DEVICE."""
+    import torch
+    build_reference_callsite()
+    result = subprocess.run([TRACK_ERROR_EXE], capture_output=True, text=True)
+    if not torch.cuda.is_available():
+        assert result.returncode == 3, (result.returncode, result.stdout, result.stderr)
+
+
+@pytest.mark.gpu
+def test_track_error_callsite_matches_the_reference():
+    """Raw clips compressed by the reference's compressor, measured by acl::calculate_compression_error with acl::decompression_context
+    and by acl_b200::calculate_compression_error with acl_b200::decompression_context (bind pose that is not the identity, scale, a
+    stripped track, full precision formats, stripped key frames, scalar float3f): same worst track and sample time, error within 5e-5
+    (scalar: exact)."""
+    if not os.path.exists(TRACK_ERROR_EXE):
+        pytest.skip("tests/cpp/_build/shim_track_error was not built (needs /root/reference at build time)")
+    result = subprocess.run([TRACK_ERROR_EXE], capture_output=True, text=True)
     assert result.returncode == 0 and "PASS" in result.stdout, (result.stdout, result.stderr)

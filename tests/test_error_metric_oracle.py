@@ -19,6 +19,25 @@ from oracle import port as P
 ERROR_TOLERANCE = 5e-5
 LANES = clips.DEFINED_LANES
 
+
+def error_tolerance(oracle_port, poses, parents) -> float:
+    """The gate scaled to the size of the poses: ERROR_TOLERANCE for object space positions up to 50 units from the root, 1e-6 of the
+    largest distance beyond (additive clips compound scales: positions reach thousands of units there)."""
+    reach = 0.0
+    for sample in range(0, poses.shape[0], max(1, poses.shape[0] // 8)):
+        obj = oracle_port.local_to_object_space(poses[sample], parents, P.NORMALIZE_IEEE)
+        reach = max(reach, float(np.max(np.abs(obj[:, 4:7]))) if obj.size else 0.0)
+    return ERROR_TOLERANCE * max(1.0, reach / 50.0)
+
+
+ADDITIVE_CASES = [("c1_30bones", 1, 60), ("c1_30bones", 2, 17), ("c1_30bones", 3, 1), ("mixed_scale", 1, 17), ("mixed_scale", 2, 1), ("mixed_scale", 3, 75),
+                  ("stripped_single", 1, 25), ("stripped_single", 3, 17), ("ragged_17", 2, 47)]
+
+
+def additive_base_spec(spec, base_samples: int):
+    import dataclasses
+    return dataclasses.replace(spec, seed=spec.seed + 777, num_samples=base_samples, scale_default_pct=40, scale_constant_pct=30)
+
 GOLDEN_TRANSFORM = [n for n in clips.TRANSFORM_SPECS if os.path.exists(clips.golden_path(n, "error.npz"))]
 GOLDEN_SCALAR = [n for n in clips.SCALAR_SPECS if os.path.exists(clips.golden_path(n, "error.npz"))]
 
@@ -75,6 +94,25 @@ def test_port_matches_live_reference_bit_for_bit(reference, oracle_port, name):
             # the same worst bone, or one the reference puts within the tolerance of its worst
             sample = int(round(ieee.sample_time * r["sample_rate"]))
             assert r["errors"][sample, ieee.index] >= r["error"] - 2 * ERROR_TOLERANCE, (name, kind)
+
+
+@pytest.mark.parametrize("name,additive_format,base_samples", ADDITIVE_CASES)
+def test_port_matches_live_reference_additive(reference, oracle_port, name, additive_format, base_samples):
+    """calculate_compression_error with an additive base (track_error.impl.h:573-680) + additive_qvvf_transform_error_metric<format>:
+    the clip measured on top of a base clip of another length, all three additive formats."""
+    spec = clips.TRANSFORM_SPECS[name]
+    r = reference.transform_error_additive(spec, clips.load_blob(name), additive_base_spec(spec, base_samples), additive_format)
+    got, errors, negative = oracle_port.transform_track_error(r["raw_poses"], r["lossy_poses"], r["sample_rate"], r["duration"], r["parents"],
+                                                              r["shell_distances"], P.NORMALIZE_RTM_SSE2, r["base_poses"], additive_format)
+    assert not negative
+    assert clips.bit_equal(errors, r["errors"])
+    assert (got.index, np.float32(got.error), np.float32(got.sample_time)) == (r["index"], np.float32(r["error"]), np.float32(r["sample_time"]))
+    applied = np.stack([oracle_port.apply_additive_to_base(additive_format, r["base_poses"][s], r["raw_poses"][s]) for s in range(spec.num_samples)])
+    tolerance = error_tolerance(oracle_port, applied, r["parents"])
+    ieee, ieee_errors, _ = oracle_port.transform_track_error(r["raw_poses"], r["lossy_poses"], r["sample_rate"], r["duration"], r["parents"],
+                                                             r["shell_distances"], P.NORMALIZE_IEEE, r["base_poses"], additive_format)
+    assert float(np.max(np.abs(ieee_errors - r["errors"]))) <= tolerance
+    assert abs(ieee.error - r["error"]) <= tolerance
 
 
 @pytest.mark.parametrize("name", GOLDEN_TRANSFORM)

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from tests import clips
-from tests.test_error_metric_oracle import ERROR_TOLERANCE, GOLDEN_SCALAR, GOLDEN_TRANSFORM, kinds_for
+from tests.test_error_metric_oracle import ADDITIVE_CASES, ERROR_TOLERANCE, GOLDEN_SCALAR, GOLDEN_TRANSFORM, additive_base_spec, error_tolerance, kinds_for
 
 pytestmark = pytest.mark.gpu
 
@@ -50,7 +50,7 @@ def _jobs(gpu, rows):
     return jobs
 
 
-def _measure(gpu, clipset, jobs, raw_poses, parents, shells, options, output_indices=None):
+def _measure(gpu, clipset, jobs, raw_poses, parents, shells, options, output_indices=None, base_poses=None):
     """Runs the call and returns (track errors structured array, error matrix [total poses][max_tracks])."""
     torch, ab, ctx = gpu["torch"], gpu["ab"], gpu["ctx"]
     total = int(jobs["num_samples"].sum())
@@ -58,7 +58,8 @@ def _measure(gpu, clipset, jobs, raw_poses, parents, shells, options, output_ind
     d_matrix = torch.full((max(total, 1), clipset.max_tracks), float("nan"), dtype=torch.float32, device="cuda")
     ctx.calculate_compression_error(clipset, jobs, _dev(gpu, raw_poses), None if parents is None else _dev(gpu, parents),
                                     None if shells is None else _dev(gpu, shells), options, d_errors,
-                                    d_output_indices=None if output_indices is None else _dev(gpu, output_indices), d_out_error_matrix=d_matrix)
+                                    d_output_indices=None if output_indices is None else _dev(gpu, output_indices), d_out_error_matrix=d_matrix,
+                                    d_base_poses=None if base_poses is None else _dev(gpu, base_poses))
     torch.cuda.synchronize()
     return d_errors.cpu().numpy().view(ab.TRACK_ERROR_DTYPE), d_matrix.cpu().numpy()
 
@@ -165,6 +166,37 @@ def test_compression_error_fast_math_within_gate(gpu):
     got, matrix = _measure(gpu, clipset, jobs, r["raw_poses"], r["parents"], r["shell_distances"], options)
     assert float(np.max(np.abs(matrix[:spec.num_samples, :spec.num_tracks] - r["errors"]))) <= 1e-3
     assert abs(float(got[0]["error"]) - r["error"]) <= 1e-3
+    clipset.release()
+
+
+@pytest.mark.parametrize("name,additive_format,base_samples", ADDITIVE_CASES)
+def test_compression_error_with_additive_base(gpu, name, additive_format, base_samples):
+    """The additive base overload (track_error.impl.h:573-680) + additive_qvvf_transform_error_metric<format>: bit for bit against the
+    oracle, within the (pose size scaled) tolerance of the live reference; measured next to a plain job of the same clip in one call."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("needs oracle/_ref/libaclref.so")
+    port = gpu["port"]
+    spec = clips.TRANSFORM_SPECS[name]
+    clipset = gpu["ctx"].upload([clips.load_blob(name)])
+    r = ref.transform_error_additive(spec, clips.load_blob(name), additive_base_spec(spec, base_samples), additive_format)
+    plain = _reference_case(name, 1)
+    common = dict(clip=0, num_samples=spec.num_samples, sample_rate=r["sample_rate"], duration=r["duration"], num_tracks=spec.num_tracks)
+    # base poses behind 2 unrelated rows; the plain job carries no additive format and must ignore them
+    base = np.concatenate([np.full((2, spec.num_tracks, 12), 7.0, np.float32), r["base_poses"]])
+    jobs = _jobs(gpu, [dict(common, additive_format=additive_format, first_base_pose=2), dict(common)])
+    got, matrix = _measure(gpu, clipset, jobs, r["raw_poses"], r["parents"], r["shell_distances"], _options(gpu, 1), base_poses=base)
+    want, want_errors, negative = port.transform_track_error(r["raw_poses"], r["lossy_poses"], r["sample_rate"], r["duration"], r["parents"],
+                                                             r["shell_distances"], port.NORMALIZE_IEEE, r["base_poses"], additive_format)
+    assert not negative and got[0]["flags"] == 0
+    assert clips.bit_equal(matrix[:spec.num_samples, :spec.num_tracks], want_errors)
+    assert (int(got[0]["index"]), np.float32(got[0]["error"]), np.float32(got[0]["sample_time"])) == (want.index, np.float32(want.error), np.float32(want.sample_time))
+    applied = np.stack([port.apply_additive_to_base(additive_format, r["base_poses"][s], r["raw_poses"][s]) for s in range(spec.num_samples)])
+    tolerance = error_tolerance(port, applied, r["parents"])
+    assert float(np.max(np.abs(matrix[:spec.num_samples, :spec.num_tracks] - r["errors"]))) <= tolerance
+    assert abs(float(got[0]["error"]) - r["error"]) <= tolerance
+    _check_against(gpu, got[1], matrix[spec.num_samples:2 * spec.num_samples, :spec.num_tracks], plain["raw_poses"], plain["lossy_poses"], plain["sample_rate"],
+                   plain["duration"], plain["parents"], plain["shell_distances"], plain, (name, "plain job next to the additive one"))
     clipset.release()
 
 
