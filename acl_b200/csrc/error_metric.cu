@@ -149,8 +149,150 @@ namespace aclb200
 			return out;
 		}
 
-		// rtm::qvv_mul(lhs, rhs), external/rtm/includes/rtm/qvvf.h:315-355, positive scale branch. `negative` reports the case the reference
-		// sends through matrices (any min(lhs.scale, rhs.scale) component < 0).
+		// ---- the negative scale branch of rtm::qvv_mul (qvvf.h:320-345): through matrices. Rare (mirrored bones), data dependent branches
+		// (quat_from_matrix), so it runs per stream on plain floats, out of line: matrix_from_qvv (matrix3x4f.h:134-159), matrix_mul (:298-321,
+		// vector_mul_add = (v0 * v1) + v2 on SSE2), matrix_remove_scale (:636-644 = vector_normalize3(axis, axis, 1e-8), vector4f.h:2310-2318),
+		// the result scale's sign bits xor-ed onto the axes, quat_from_matrix (impl/matrix_affine_common.h:153-227, its closing
+		// quat_normalize with the IEEE 1 / sqrt like every normalisation here) ----
+		struct Matrix3x4 { float m[4][3]; };
+
+		__device__ __forceinline__ Matrix3x4 matrix_from_qvv(const Qvv<float>& q)
+		{
+			const Fp<float> fp{ 1.0f };
+			const float x2 = fp.add(q.rotation.x, q.rotation.x), y2 = fp.add(q.rotation.y, q.rotation.y), z2 = fp.add(q.rotation.z, q.rotation.z);
+			const float xx = fp.mul(q.rotation.x, x2), xy = fp.mul(q.rotation.x, y2), xz = fp.mul(q.rotation.x, z2);
+			const float yy = fp.mul(q.rotation.y, y2), yz = fp.mul(q.rotation.y, z2), zz = fp.mul(q.rotation.z, z2);
+			const float wx = fp.mul(q.rotation.w, x2), wy = fp.mul(q.rotation.w, y2), wz = fp.mul(q.rotation.w, z2);
+			Matrix3x4 out;
+			out.m[0][0] = fp.mul(fp.sub(1.0f, fp.add(yy, zz)), q.scale.x);	out.m[0][1] = fp.mul(fp.add(xy, wz), q.scale.x);				out.m[0][2] = fp.mul(fp.sub(xz, wy), q.scale.x);
+			out.m[1][0] = fp.mul(fp.sub(xy, wz), q.scale.y);				out.m[1][1] = fp.mul(fp.sub(1.0f, fp.add(xx, zz)), q.scale.y);	out.m[1][2] = fp.mul(fp.add(yz, wx), q.scale.y);
+			out.m[2][0] = fp.mul(fp.add(xz, wy), q.scale.z);				out.m[2][1] = fp.mul(fp.sub(yz, wx), q.scale.z);				out.m[2][2] = fp.mul(fp.sub(1.0f, fp.add(xx, yy)), q.scale.z);
+			out.m[3][0] = q.translation.x;									out.m[3][1] = q.translation.y;									out.m[3][2] = q.translation.z;
+			return out;
+		}
+
+		__device__ __noinline__ void qvv_mul_negative_scale(const Qvv<float>* lhs_in, const Qvv<float>* rhs_in, Qvv<float>* out)
+		{
+			const Fp<float> fp{ 1.0f };
+			const Qvv<float> lhs = *lhs_in, rhs = *rhs_in;
+			const Matrix3x4 l = matrix_from_qvv(lhs), r = matrix_from_qvv(rhs);
+			float m[4][3];
+			#pragma unroll
+			for (int row = 0; row < 4; ++row)
+				#pragma unroll
+				for (int c = 0; c < 3; ++c)
+				{
+					float tmp = fp.mul(l.m[row][0], r.m[0][c]);
+					tmp = fp.add(fp.mul(l.m[row][1], r.m[1][c]), tmp);
+					tmp = fp.add(fp.mul(l.m[row][2], r.m[2][c]), tmp);
+					m[row][c] = row == 3 ? fp.add(r.m[3][c], tmp) : tmp;
+				}
+			const float scale[3] = { fp.mul(lhs.scale.x, rhs.scale.x), fp.mul(lhs.scale.y, rhs.scale.y), fp.mul(lhs.scale.z, rhs.scale.z) };
+			#pragma unroll
+			for (int axis = 0; axis < 3; ++axis)
+			{
+				const float len_sq = fp.add(fp.add(fp.mul(m[axis][0], m[axis][0]), fp.mul(m[axis][1], m[axis][1])), fp.mul(m[axis][2], m[axis][2]));
+				const float inv_len = len_sq >= 1.0e-8f ? fp.inv_sqrt(len_sq) : 1.0f;
+				const uint32_t sign = __float_as_uint(scale[axis]) & 0x80000000u;
+				#pragma unroll
+				for (int c = 0; c < 3; ++c)
+				{
+					const float normalized = len_sq >= 1.0e-8f ? fp.mul(m[axis][c], inv_len) : m[axis][c];
+					m[axis][c] = __uint_as_float(__float_as_uint(normalized) ^ sign);
+				}
+			}
+
+			Quat<float> q;
+			bool zero_axis = false;
+			#pragma unroll
+			for (int axis = 0; axis < 3; ++axis)
+				zero_axis = zero_axis || (fabsf(m[axis][0]) <= 0.00001f && fabsf(m[axis][1]) <= 0.00001f && fabsf(m[axis][2]) <= 0.00001f);
+			const float trace = fp.add(fp.add(m[0][0], m[1][1]), m[2][2]);
+			if (zero_axis)
+				q = Quat<float>{ 0.0f, 0.0f, 0.0f, 1.0f };		// Zero scale not supported, return the identity
+			else if (trace > 0.0f)
+			{
+				const float inv_trace = fp.inv_sqrt(fp.add(trace, 1.0f));
+				const float half_inv_trace = fp.mul(inv_trace, 0.5f);
+				q.x = fp.mul(fp.sub(m[1][2], m[2][1]), half_inv_trace);
+				q.y = fp.mul(fp.sub(m[2][0], m[0][2]), half_inv_trace);
+				q.z = fp.mul(fp.sub(m[0][1], m[1][0]), half_inv_trace);
+				q.w = fp.mul(__fdiv_rn(1.0f, inv_trace), 0.5f);
+				q = quat_normalize(fp, q);
+			}
+			else
+			{
+				// best axis = the largest diagonal element; the three cases are the reference's index arithmetic written out
+				const int best = m[2][2] > (m[1][1] > m[0][0] ? m[1][1] : m[0][0]) ? 2 : (m[1][1] > m[0][0] ? 1 : 0);
+				float d_best, d_next, d_next_next, s_next, s_next_next, s_w;
+				if (best == 0)		{ d_best = m[0][0]; d_next = m[1][1]; d_next_next = m[2][2]; s_next = fp.add(m[0][1], m[1][0]); s_next_next = fp.add(m[0][2], m[2][0]); s_w = fp.sub(m[1][2], m[2][1]); }
+				else if (best == 1)	{ d_best = m[1][1]; d_next = m[2][2]; d_next_next = m[0][0]; s_next = fp.add(m[1][2], m[2][1]); s_next_next = fp.add(m[1][0], m[0][1]); s_w = fp.sub(m[2][0], m[0][2]); }
+				else				{ d_best = m[2][2]; d_next = m[0][0]; d_next_next = m[1][1]; s_next = fp.add(m[2][0], m[0][2]); s_next_next = fp.add(m[2][1], m[1][2]); s_w = fp.sub(m[0][1], m[1][0]); }
+				const float pseudo_trace = fp.sub(fp.sub(fp.add(1.0f, d_best), d_next), d_next_next);
+				const float inv_pseudo_trace = fp.inv_sqrt(pseudo_trace);
+				const float half_inv_pseudo_trace = fp.mul(inv_pseudo_trace, 0.5f);
+				const float v_best = fp.mul(__fdiv_rn(1.0f, inv_pseudo_trace), 0.5f);
+				const float v_next = fp.mul(half_inv_pseudo_trace, s_next);
+				const float v_next_next = fp.mul(half_inv_pseudo_trace, s_next_next);
+				q.w = fp.mul(half_inv_pseudo_trace, s_w);
+				if (best == 0)		{ q.x = v_best; q.y = v_next; q.z = v_next_next; }
+				else if (best == 1)	{ q.y = v_best; q.z = v_next; q.x = v_next_next; }
+				else				{ q.z = v_best; q.x = v_next; q.y = v_next_next; }
+				q = quat_normalize(fp, q);
+			}
+			Qvv<float> result;
+			result.rotation = q;
+			result.translation = Vec3<float>{ m[3][0], m[3][1], m[3][2] };
+			result.scale = Vec3<float>{ scale[0], scale[1], scale[2] };
+			*out = result;
+		}
+
+		__device__ __forceinline__ Qvv<float> stream_of(const Qvv<float2>& q, int stream)
+		{
+			const auto pick = [stream](float2 v) { return stream == 0 ? v.x : v.y; };
+			Qvv<float> out;
+			out.rotation = Quat<float>{ pick(q.rotation.x), pick(q.rotation.y), pick(q.rotation.z), pick(q.rotation.w) };
+			out.translation = Vec3<float>{ pick(q.translation.x), pick(q.translation.y), pick(q.translation.z) };
+			out.scale = Vec3<float>{ pick(q.scale.x), pick(q.scale.y), pick(q.scale.z) };
+			return out;
+		}
+
+		__device__ __forceinline__ void set_stream(Qvv<float2>& q, int stream, const Qvv<float>& value)
+		{
+			const auto put = [stream](float2& v, float a) { if (stream == 0) v.x = a; else v.y = a; };
+			put(q.rotation.x, value.rotation.x); put(q.rotation.y, value.rotation.y); put(q.rotation.z, value.rotation.z); put(q.rotation.w, value.rotation.w);
+			put(q.translation.x, value.translation.x); put(q.translation.y, value.translation.y); put(q.translation.z, value.translation.z);
+			put(q.scale.x, value.scale.x); put(q.scale.y, value.scale.y); put(q.scale.z, value.scale.z);
+		}
+
+		__device__ __forceinline__ bool stream_is_negative(const Qvv<float>& lhs, const Qvv<float>& rhs)
+		{
+			return fminf(lhs.scale.x, rhs.scale.x) < 0.0f || fminf(lhs.scale.y, rhs.scale.y) < 0.0f || fminf(lhs.scale.z, rhs.scale.z) < 0.0f;
+		}
+
+		// replaces the streams of `out` (the positive branch's result) whose operands have a negative scale
+		__device__ __forceinline__ void redo_negative_streams(Qvv<float>& out, const Qvv<float>& lhs, const Qvv<float>& rhs)
+		{
+			qvv_mul_negative_scale(&lhs, &rhs, &out);
+		}
+
+		__device__ __forceinline__ void redo_negative_streams(Qvv<float2>& out, const Qvv<float2>& lhs, const Qvv<float2>& rhs)
+		{
+			#pragma unroll
+			for (int stream = 0; stream < 2; ++stream)
+			{
+				const Qvv<float> l = stream_of(lhs, stream), r = stream_of(rhs, stream);
+				if (stream_is_negative(l, r))
+				{
+					Qvv<float> redone;
+					qvv_mul_negative_scale(&l, &r, &redone);
+					set_stream(out, stream, redone);
+				}
+			}
+		}
+
+		// rtm::qvv_mul(lhs, rhs), external/rtm/includes/rtm/qvvf.h:315-355. `negative` reports that a stream went through the matrix branch
+		// (any min(lhs.scale, rhs.scale) component < 0).
 		template<class V>
 		__device__ __forceinline__ Qvv<V> qvv_mul(const Fp<V>& fp, const Qvv<V>& lhs, const Qvv<V>& rhs, bool& negative)
 		{
@@ -168,6 +310,8 @@ namespace aclb200
 			out.scale.x = fp.mul(lhs.scale.x, rhs.scale.x);
 			out.scale.y = fp.mul(lhs.scale.y, rhs.scale.y);
 			out.scale.z = fp.mul(lhs.scale.z, rhs.scale.z);
+			if (negative)
+				redo_negative_streams(out, lhs, rhs);
 			return out;
 		}
 

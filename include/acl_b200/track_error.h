@@ -11,7 +11,6 @@
 // Differences from the reference, all reported (never silent):
 //   * acl::qvvf_transform_error_metric and acl::additive_qvvf_transform_error_metric<format> (with the additive base overload) are
 //     implemented on the device; another metric (qvvf_matrix3x4f_transform_error_metric) throws acl_b200::error (ACLB200_ERR_UNSUPPORTED);
-//   * a negative scale somewhere in a pose (rtm::qvv_mul's matrix branch) throws acl_b200::error (ACLB200_ERR_UNSUPPORTED);
 //   * rtm::quat_normalize starts from the CPU's rsqrtss estimate in the reference: errors agree within 5e-5 on poses tens of units
 //     across (measured 1e-5), the worst track and its sample time are the reference's whenever its lead exceeds that.
 #pragma once
@@ -159,8 +158,6 @@ namespace acl_b200
 				is_transform ? static_cast<const uint32_t*>(d_outputs.get(device, 0)) : nullptr, has_base ? d_base.get(device, 0) : nullptr, &options, d_out, nullptr, nullptr), "aclb200_calculate_compression_error");
 			aclb200_track_error result;
 			device.check(aclb200_copy_to_host(device.get(), &result, d_out, sizeof(result)), "result download");
-			if ((result.flags & ACLB200_ERROR_FLAG_NEGATIVE_SCALE) != 0)
-				throw error(ACLB200_ERR_UNSUPPORTED, "calculate_compression_error: a negative scale takes rtm::qvv_mul through matrices, which the device path does not implement");
 			if ((result.flags & ACLB200_ERROR_FLAG_INVALID_SKELETON) != 0)
 				throw error(ACLB200_ERR_INVALID_ARGUMENT, "calculate_compression_error: a parent track does not precede its child");
 

@@ -236,7 +236,7 @@ ACLB200_API aclb200_status aclb200_decompress_tracks_host(aclb200_context* conte
 
 /* ---- the nearest callers of the decode path, on the device (acl_b200/csrc/error_metric.cu) ---------------- */
 
-/* acl::track_error (compression/track_error.h:48-62) + what this library could not follow the reference through */
+/* acl::track_error (compression/track_error.h:48-62) + what the measurement met on the way */
 typedef struct aclb200_track_error
 {
 	uint32_t index;					/* track with the worst error (0xFFFFFFFF when nothing was measured) */
@@ -247,8 +247,7 @@ typedef struct aclb200_track_error
 
 enum
 {
-	ACLB200_ERROR_FLAG_NEGATIVE_SCALE = 1,		/* a negative scale met rtm::qvv_mul's matrix branch (qvvf.h:320-345), which is not implemented: the
-												 * clip's numbers are NOT the reference's */
+	ACLB200_ERROR_FLAG_NEGATIVE_SCALE = 1,		/* informational: a negative scale took rtm::qvv_mul through its matrix branch (qvvf.h:320-345) somewhere */
 	ACLB200_ERROR_FLAG_INVALID_SKELETON = 2		/* a parent index does not precede its child (the reference reads an unwritten transform there):
 												 * the bone was treated as a root */
 };

@@ -1409,8 +1409,107 @@ static void metric_quat_normalize(float q[4], int normalize_mode)
 		q[i] = q[i] * inv_len;
 }
 
-/* rtm::qvv_normalize(rtm::qvv_mul(local, parent_object)), qvvf.h:315-355,426-430: the positive scale branch. Returns 1 when the
- * reference would take the negative scale branch (through matrices), which this port does not restate. */
+/* rtm::matrix_from_qvv, matrix3x4f.h:134-159: rows x_axis, y_axis, z_axis (xyz), w_axis = translation */
+static void rtm_matrix_from_qvv(const float q[12], float m[4][3])
+{
+	const float x2 = q[0] + q[0], y2 = q[1] + q[1], z2 = q[2] + q[2];
+	const float xx = q[0] * x2, xy = q[0] * y2, xz = q[0] * z2;
+	const float yy = q[1] * y2, yz = q[1] * z2, zz = q[2] * z2;
+	const float wx = q[3] * x2, wy = q[3] * y2, wz = q[3] * z2;
+	m[0][0] = (1.0f - (yy + zz)) * q[8];	m[0][1] = (xy + wz) * q[8];				m[0][2] = (xz - wy) * q[8];
+	m[1][0] = (xy - wz) * q[9];				m[1][1] = (1.0f - (xx + zz)) * q[9];	m[1][2] = (yz + wx) * q[9];
+	m[2][0] = (xz + wy) * q[10];			m[2][1] = (yz - wx) * q[10];			m[2][2] = (1.0f - (xx + yy)) * q[10];
+	m[3][0] = q[4];							m[3][1] = q[5];							m[3][2] = q[6];
+}
+
+/* rtm_impl::quat_from_matrix, impl/matrix_affine_common.h:153-227 (float overloads of scalar_sqrt_reciprocal / scalar_reciprocal:
+ * 1 / sqrt, 1 / x, scalarf.h:294-325), ending in rtm::quat_normalize */
+static void rtm_quat_from_matrix(float m[3][3], int normalize_mode, float out[4])
+{
+	for (int axis = 0; axis < 3; ++axis)
+		if (fabsf(m[axis][0]) <= 0.00001f && fabsf(m[axis][1]) <= 0.00001f && fabsf(m[axis][2]) <= 0.00001f)
+		{
+			out[0] = 0.0f; out[1] = 0.0f; out[2] = 0.0f; out[3] = 1.0f;		/* Zero scale not supported, return the identity */
+			return;
+		}
+	const float trace = m[0][0] + m[1][1] + m[2][2];
+	float q[4];
+	if (trace > 0.0f)
+	{
+		const float inv_trace = 1.0f / sqrtf(trace + 1.0f);
+		const float half_inv_trace = inv_trace * 0.5f;
+		q[0] = (m[1][2] - m[2][1]) * half_inv_trace;
+		q[1] = (m[2][0] - m[0][2]) * half_inv_trace;
+		q[2] = (m[0][1] - m[1][0]) * half_inv_trace;
+		q[3] = (1.0f / inv_trace) * 0.5f;
+	}
+	else
+	{
+		int best = 0;
+		if (m[1][1] > m[0][0])
+			best = 1;
+		if (m[2][2] > m[best][best])
+			best = 2;
+		const int next = (best + 1) % 3;
+		const int next_next = (next + 1) % 3;
+		const float pseudo_trace = 1.0f + m[best][best] - m[next][next] - m[next_next][next_next];
+		const float inv_pseudo_trace = 1.0f / sqrtf(pseudo_trace);
+		const float half_inv_pseudo_trace = inv_pseudo_trace * 0.5f;
+		q[best] = (1.0f / inv_pseudo_trace) * 0.5f;
+		q[next] = half_inv_pseudo_trace * (m[best][next] + m[next][best]);
+		q[next_next] = half_inv_pseudo_trace * (m[best][next_next] + m[next_next][best]);
+		q[3] = half_inv_pseudo_trace * (m[next][next_next] - m[next_next][next]);
+	}
+	metric_quat_normalize(q, normalize_mode);
+	memcpy(out, q, sizeof(q));
+}
+
+/* The negative scale branch of rtm::qvv_mul, qvvf.h:320-345: through matrices (matrix_mul matrix3x4f.h:298-321 with
+ * vector_mul_add = (v0 * v1) + v2 on SSE2, matrix_remove_scale :636-644 = vector_normalize3(axis, axis, 1e-8) vector4f.h:2310-2318,
+ * the result's sign bits xor-ed onto the axes) */
+static void qvv_mul_negative_scale(const float lhs[12], const float rhs[12], int normalize_mode, float out[12])
+{
+	float l[4][3], r[4][3], m[4][3];
+	rtm_matrix_from_qvv(lhs, l);
+	rtm_matrix_from_qvv(rhs, r);
+	for (int row = 0; row < 4; ++row)
+		for (int c = 0; c < 3; ++c)
+		{
+			float tmp = l[row][0] * r[0][c];
+			tmp = l[row][1] * r[1][c] + tmp;
+			tmp = l[row][2] * r[2][c] + tmp;
+			m[row][c] = row == 3 ? r[3][c] + tmp : tmp;
+		}
+	float scale[3];
+	for (int i = 0; i < 3; ++i)
+		scale[i] = lhs[8 + i] * rhs[8 + i];
+	for (int axis = 0; axis < 3; ++axis)
+	{
+		const float len_sq = (m[axis][0] * m[axis][0] + m[axis][1] * m[axis][1]) + m[axis][2] * m[axis][2];
+		if (len_sq >= 1.0e-8f)
+		{
+			const float inv_len = 1.0f / sqrtf(len_sq);
+			for (int c = 0; c < 3; ++c)
+				m[axis][c] = m[axis][c] * inv_len;
+		}
+		const uint32_t sign = f32_as_u32(scale[axis]) & 0x80000000u;
+		for (int c = 0; c < 3; ++c)
+			m[axis][c] = u32_as_f32(f32_as_u32(m[axis][c]) ^ sign);
+	}
+	float result[12];
+	rtm_quat_from_matrix(m, normalize_mode, result);
+	for (int i = 0; i < 3; ++i)
+	{
+		result[4 + i] = m[3][i];
+		result[8 + i] = scale[i];
+	}
+	result[7] = 0.0f;
+	result[11] = 0.0f;
+	memcpy(out, result, sizeof(result));
+}
+
+/* rtm::qvv_normalize(rtm::qvv_mul(local, parent_object)), qvvf.h:315-355,426-430. Returns 1 when the negative scale branch (through
+ * matrices) was taken. */
 static int qvv_mul_normalize(const float local[12], const float parent[12], int normalize_mode, float out[12])
 {
 	int negative = 0;
@@ -1419,26 +1518,30 @@ static int qvv_mul_normalize(const float local[12], const float parent[12], int 
 		const float min_scale = local[8 + i] < parent[8 + i] ? local[8 + i] : parent[8 + i];	/* _mm_min_ps(lhs, rhs) */
 		negative |= min_scale < 0.0f;
 	}
-	float rotation[4];
-	rtm_quat_mul(local + 0, parent + 0, rotation);
-	const float scaled[3] = { local[4] * parent[8], local[5] * parent[9], local[6] * parent[10] };
-	float rotated[3];
-	rtm_quat_mul_vector3(scaled, parent + 0, rotated);
-	metric_quat_normalize(rotation, normalize_mode);
-	for (int i = 0; i < 4; ++i)
-		out[i] = rotation[i];
-	for (int i = 0; i < 3; ++i)
+	float result[12];
+	if (negative)
+		qvv_mul_negative_scale(local, parent, normalize_mode, result);
+	else
 	{
-		out[4 + i] = rotated[i] + parent[4 + i];
-		out[8 + i] = local[8 + i] * parent[8 + i];
+		rtm_quat_mul(local + 0, parent + 0, result);
+		const float scaled[3] = { local[4] * parent[8], local[5] * parent[9], local[6] * parent[10] };
+		float rotated[3];
+		rtm_quat_mul_vector3(scaled, parent + 0, rotated);
+		for (int i = 0; i < 3; ++i)
+		{
+			result[4 + i] = rotated[i] + parent[4 + i];
+			result[8 + i] = local[8 + i] * parent[8 + i];
+		}
+		result[7] = 0.0f;
+		result[11] = 0.0f;
 	}
-	out[7] = 0.0f;
-	out[11] = 0.0f;
+	metric_quat_normalize(result, normalize_mode);		/* qvv_normalize, qvvf.h:426-430 */
+	memcpy(out, result, sizeof(result));
 	return negative;
 }
 
-/* rtm::qvv_mul(lhs, rhs), qvvf.h:315-355, positive scale branch, no normalisation. Returns 1 for the negative scale branch. */
-static int qvv_mul_plain(const float lhs[12], const float rhs[12], float out[12])
+/* rtm::qvv_mul(lhs, rhs), qvvf.h:315-355, no normalisation on top. Returns 1 when the negative scale branch was taken. */
+static int qvv_mul_plain(const float lhs[12], const float rhs[12], int normalize_mode, float out[12])
 {
 	int negative = 0;
 	for (int i = 0; i < 3; ++i)
@@ -1446,29 +1549,31 @@ static int qvv_mul_plain(const float lhs[12], const float rhs[12], float out[12]
 		const float min_scale = lhs[8 + i] < rhs[8 + i] ? lhs[8 + i] : rhs[8 + i];
 		negative |= min_scale < 0.0f;
 	}
-	float rotation[4];
-	rtm_quat_mul(lhs + 0, rhs + 0, rotation);
-	const float scaled[3] = { lhs[4] * rhs[8], lhs[5] * rhs[9], lhs[6] * rhs[10] };
-	float rotated[3];
-	rtm_quat_mul_vector3(scaled, rhs + 0, rotated);
 	float result[12];
-	for (int i = 0; i < 4; ++i)
-		result[i] = rotation[i];
-	for (int i = 0; i < 3; ++i)
+	if (negative)
+		qvv_mul_negative_scale(lhs, rhs, normalize_mode, result);
+	else
 	{
-		result[4 + i] = rotated[i] + rhs[4 + i];
-		result[8 + i] = lhs[8 + i] * rhs[8 + i];
+		rtm_quat_mul(lhs + 0, rhs + 0, result);
+		const float scaled[3] = { lhs[4] * rhs[8], lhs[5] * rhs[9], lhs[6] * rhs[10] };
+		float rotated[3];
+		rtm_quat_mul_vector3(scaled, rhs + 0, rotated);
+		for (int i = 0; i < 3; ++i)
+		{
+			result[4 + i] = rotated[i] + rhs[4 + i];
+			result[8 + i] = lhs[8 + i] * rhs[8 + i];
+		}
+		result[7] = 0.0f;
+		result[11] = 0.0f;
 	}
-	result[7] = 0.0f;
-	result[11] = 0.0f;
 	memcpy(out, result, sizeof(result));
 	return negative;
 }
 
 /* acl::apply_additive_to_base(format, base, additive), core/additive_utils.h:131-167, over a pose, in place on `pose` (the additive one):
  * 0 none, 1 relative = qvv_mul(additive, base), 2 additive0 (scale = additive * base), 3 additive1 (scale = (1 + additive) * base).
- * Returns 1 when `relative` met a negative scale. */
-int aclo_apply_additive_to_base(uint32_t additive_format, const float* base_pose, float* pose, uint32_t num_tracks)
+ * Returns 1 when `relative` went through rtm::qvv_mul's negative scale branch (whose quat_from_matrix normalises: normalize_mode). */
+int aclo_apply_additive_to_base(uint32_t additive_format, const float* base_pose, float* pose, uint32_t num_tracks, int normalize_mode)
 {
 	int negative = 0;
 	for (uint32_t bone = 0; bone < num_tracks; ++bone)
@@ -1476,7 +1581,7 @@ int aclo_apply_additive_to_base(uint32_t additive_format, const float* base_pose
 		const float* base = base_pose + (size_t)bone * 12;
 		float* additive = pose + (size_t)bone * 12;
 		if (additive_format == 1)
-			negative |= qvv_mul_plain(additive, base, additive);
+			negative |= qvv_mul_plain(additive, base, normalize_mode, additive);
 		else if (additive_format == 2 || additive_format == 3)
 		{
 			float rotation[4];
@@ -1549,7 +1654,7 @@ float aclo_calculate_error(const float* raw_object_bone, const float* lossy_obje
  * raw_poses = raw_tracks.sample_tracks(t_i), lossy_poses = seek(t_i) + decompress_tracks (already remapped, :341), both
  * [num_samples][num_tracks][12]; t_i = min(i / sample_rate, duration) (:337). base_poses (optional): the additive base sampled at the matching
  * times (:352-356), applied to both poses with `additive_format` (:358-359). out_errors (optional):
- * [num_samples][num_tracks]. Returns < 0 for an invalid skeleton order, 1 if a negative scale was met (result not the reference's). */
+ * [num_samples][num_tracks]. Returns < 0 for an invalid skeleton order, 1 if a negative scale took rtm::qvv_mul through matrices (informational). */
 int aclo_transform_track_error(const float* raw_poses, const float* lossy_poses, uint32_t num_samples, uint32_t num_tracks,
 	float sample_rate, float duration, const uint32_t* parent_indices, const float* shell_distances, int normalize_mode,
 	aclo_track_error* out_error, float* out_errors, float* scratch_object_poses /* [4][num_tracks][12] */,
@@ -1579,8 +1684,8 @@ int aclo_transform_track_error(const float* raw_poses, const float* lossy_poses,
 			float* lossy_applied = scratch_object_poses + (size_t)num_tracks * 36;
 			memcpy(raw_applied, raw_local, (size_t)num_tracks * 12 * sizeof(float));
 			memcpy(lossy_applied, lossy_local, (size_t)num_tracks * 12 * sizeof(float));
-			negative |= aclo_apply_additive_to_base(additive_format, base_poses + pose, raw_applied, num_tracks);
-			negative |= aclo_apply_additive_to_base(additive_format, base_poses + pose, lossy_applied, num_tracks);
+			negative |= aclo_apply_additive_to_base(additive_format, base_poses + pose, raw_applied, num_tracks, normalize_mode);
+			negative |= aclo_apply_additive_to_base(additive_format, base_poses + pose, lossy_applied, num_tracks, normalize_mode);
 			raw_local = raw_applied;
 			lossy_local = lossy_applied;
 		}

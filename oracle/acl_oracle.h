@@ -131,8 +131,8 @@ typedef struct aclo_track_error		/* acl::track_error, compression/track_error.h:
 	float    sample_time;
 } aclo_track_error;
 
-/* poses are [num_tracks][12] floats (rtm::qvvf). Returns < 0 when a parent does not precede its child, 1 when a negative scale was met
- * (the reference then goes through matrices, qvvf.h:320-345: not restated), else 0. */
+/* poses are [num_tracks][12] floats (rtm::qvvf). Returns < 0 when a parent does not precede its child, 1 when a negative scale took
+ * rtm::qvv_mul through its matrix branch (qvvf.h:320-345, restated as well; informational), else 0. */
 int aclo_local_to_object_space(const float* local_pose, const uint32_t* parent_indices, uint32_t num_tracks, int normalize_mode, float* out_object_pose);
 float aclo_calculate_error(const float* raw_object_bone, const float* lossy_object_bone, float shell_distance);
 int aclo_transform_track_error(const float* raw_poses, const float* lossy_poses, uint32_t num_samples, uint32_t num_tracks,
@@ -140,7 +140,7 @@ int aclo_transform_track_error(const float* raw_poses, const float* lossy_poses,
 	aclo_track_error* out_error, float* out_errors, float* scratch_object_poses /* [4][num_tracks][12] */,
 	const float* base_poses /* optional additive base, [num_samples][num_tracks][12] */, uint32_t additive_format);
 /* acl::apply_additive_to_base (core/additive_utils.h:131-167) over a pose, in place on `pose`; format = acl::additive_clip_format8 */
-int aclo_apply_additive_to_base(uint32_t additive_format, const float* base_pose, float* pose, uint32_t num_tracks);
+int aclo_apply_additive_to_base(uint32_t additive_format, const float* base_pose, float* pose, uint32_t num_tracks, int normalize_mode);
 int aclo_scalar_track_error(const float* raw_values, const float* lossy_values, uint32_t num_samples, uint32_t num_tracks, uint32_t components,
 	float sample_rate, float duration, aclo_track_error* out_error);
 

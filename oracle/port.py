@@ -279,13 +279,13 @@ def transform_track_error(raw_poses: np.ndarray, lossy_poses: np.ndarray, sample
     return result, errors, rc == 1
 
 
-def apply_additive_to_base(additive_format: int, base_pose: np.ndarray, pose: np.ndarray) -> np.ndarray:
+def apply_additive_to_base(additive_format: int, base_pose: np.ndarray, pose: np.ndarray, normalize_mode: int = NORMALIZE_IEEE) -> np.ndarray:
     """acl::apply_additive_to_base over one pose [num_tracks][12]; returns the combined pose."""
     base_pose = np.ascontiguousarray(base_pose, dtype=np.float32)
     out = np.array(pose, dtype=np.float32, order="C", copy=True)
     fn = lib().aclo_apply_additive_to_base
-    fn.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
-    fn(additive_format, base_pose.ctypes.data, out.ctypes.data, out.shape[0])
+    fn.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]
+    fn(additive_format, base_pose.ctypes.data, out.ctypes.data, out.shape[0], normalize_mode)
     return out
 
 

@@ -46,6 +46,7 @@ class _TransformSpec(C.Structure):
         ("rotation_format", C.c_uint32), ("translation_format", C.c_uint32), ("scale_format", C.c_uint32),
         ("level", C.c_uint32), ("optimize_loops", C.c_uint32), ("strip_trivial", C.c_uint32),
         ("strip_proportion", C.c_float), ("strip_threshold", C.c_float), ("rotation_offset", C.c_float),
+        ("negative_scale_pct", C.c_uint32),
     ]
 
 
@@ -93,6 +94,7 @@ class TransformSpec:
     strip_proportion: float = 0.0
     strip_threshold: float = 0.0
     rotation_offset: float = 0.0
+    negative_scale_pct: int = 0
 
     def to_c(self) -> _TransformSpec:
         return _TransformSpec(**asdict(self))

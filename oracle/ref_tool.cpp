@@ -94,6 +94,7 @@ extern "C"
 		float    strip_proportion;
 		float    strip_threshold;
 		float    rotation_offset;		// radians added to every animated rotation angle (pi => W crosses 0, the ill-conditioned end of W reconstruction)
+		uint32_t negative_scale_pct;	// bones whose scale.x is mirrored (rtm::qvv_mul's matrix branch in the error metric); consumes no random numbers
 	};
 
 	struct aclref_scalar_spec
@@ -263,6 +264,9 @@ namespace
 					}
 					transform.scale = rtm::vector_set(float(v[0]), float(v[1]), float(v[2]), 0.0F);
 				}
+
+				if ((bone * 7u + 3u) % 100u < spec.negative_scale_pct)
+					transform.scale = rtm::vector_mul(transform.scale, rtm::vector_set(-1.0F, 1.0F, 1.0F, 0.0F));
 
 				track[sample] = transform;
 			}

@@ -115,6 +115,40 @@ def test_port_matches_live_reference_additive(reference, oracle_port, name, addi
     assert abs(ieee.error - r["error"]) <= tolerance
 
 
+MIRRORED_CASES = [("mixed_scale", 30), ("c1_30bones", 20), ("ragged_17", 50), ("single_segment", 100)]
+
+
+def mirrored_spec(name: str, negative_scale_pct: int):
+    """A named clip with scale.x mirrored on some bones: their children go through rtm::qvv_mul's matrix branch (qvvf.h:320-345)."""
+    import dataclasses
+    spec = clips.TRANSFORM_SPECS[name]
+    return dataclasses.replace(spec, negative_scale_pct=negative_scale_pct, scale_default_pct=min(spec.scale_default_pct, 60))
+
+
+@pytest.mark.parametrize("name,negative_scale_pct", MIRRORED_CASES)
+def test_port_matches_live_reference_negative_scale(reference, oracle_port, name, negative_scale_pct):
+    spec = mirrored_spec(name, negative_scale_pct)
+    blob = reference.compress_transform(spec)
+    r = reference.transform_error(spec, blob, 1)
+    assert r["raw_poses"][..., 8:11].min() < 0.0
+    got, errors, negative = oracle_port.transform_track_error(r["raw_poses"], r["lossy_poses"], r["sample_rate"], r["duration"], r["parents"],
+                                                              r["shell_distances"], P.NORMALIZE_RTM_SSE2)
+    assert negative
+    for sample in range(0, spec.num_samples, 7):
+        obj = oracle_port.local_to_object_space(r["lossy_poses"][sample], r["parents"], P.NORMALIZE_RTM_SSE2)
+        assert clips.bit_equal(obj[:, LANES], r["object_poses"][1, sample][:, LANES]), (name, sample)
+    assert clips.bit_equal(errors, r["errors"])
+    assert (got.index, np.float32(got.error), np.float32(got.sample_time)) == (r["index"], np.float32(r["error"]), np.float32(r["sample_time"]))
+    ieee, ieee_errors, _ = oracle_port.transform_track_error(r["raw_poses"], r["lossy_poses"], r["sample_rate"], r["duration"], r["parents"],
+                                                             r["shell_distances"], P.NORMALIZE_IEEE)
+    assert float(np.max(np.abs(ieee_errors - r["errors"]))) <= error_tolerance(oracle_port, r["raw_poses"], r["parents"])
+    # the relative additive format multiplies through rtm::qvv_mul as well
+    ra = reference.transform_error_additive(spec, blob, additive_base_spec(spec, 17), 1)
+    got, errors, negative = oracle_port.transform_track_error(ra["raw_poses"], ra["lossy_poses"], ra["sample_rate"], ra["duration"], ra["parents"],
+                                                              ra["shell_distances"], P.NORMALIZE_RTM_SSE2, ra["base_poses"], 1)
+    assert negative and clips.bit_equal(errors, ra["errors"])
+
+
 @pytest.mark.parametrize("name", GOLDEN_TRANSFORM)
 def test_port_matches_golden_errors(oracle_port, name):
     blob = clips.load_blob(name)

@@ -12,7 +12,8 @@ import numpy as np
 import pytest
 
 from tests import clips
-from tests.test_error_metric_oracle import ADDITIVE_CASES, ERROR_TOLERANCE, GOLDEN_SCALAR, GOLDEN_TRANSFORM, additive_base_spec, error_tolerance, kinds_for
+from tests.test_error_metric_oracle import (ADDITIVE_CASES, ERROR_TOLERANCE, GOLDEN_SCALAR, GOLDEN_TRANSFORM, MIRRORED_CASES, additive_base_spec,
+                                            error_tolerance, kinds_for, mirrored_spec)
 
 pytestmark = pytest.mark.gpu
 
@@ -200,6 +201,42 @@ def test_compression_error_with_additive_base(gpu, name, additive_format, base_s
     clipset.release()
 
 
+@pytest.mark.parametrize("name,negative_scale_pct", MIRRORED_CASES)
+def test_compression_error_with_negative_scales(gpu, name, negative_scale_pct):
+    """Mirrored bones: rtm::qvv_mul's matrix branch (matrix_from_qvv, matrix_mul, matrix_remove_scale, quat_from_matrix) on the device,
+    per stream, bit for bit against the oracle; also under the relative additive format, and through aclb200_local_to_object_space."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("needs oracle/_ref/libaclref.so")
+    torch, ab, ctx, port = gpu["torch"], gpu["ab"], gpu["ctx"], gpu["port"]
+    spec = mirrored_spec(name, negative_scale_pct)
+    blob = ref.compress_transform(spec)
+    clipset = ctx.upload([blob], check_hash=True)
+    r = ref.transform_error(spec, blob, 1)
+    ra = ref.transform_error_additive(spec, blob, additive_base_spec(spec, 17), 1)
+    common = dict(clip=0, num_samples=spec.num_samples, sample_rate=r["sample_rate"], duration=r["duration"], num_tracks=spec.num_tracks)
+    jobs = _jobs(gpu, [dict(common), dict(common, additive_format=1)])
+    got, matrix = _measure(gpu, clipset, jobs, r["raw_poses"], r["parents"], r["shell_distances"], _options(gpu, 1), base_poses=ra["base_poses"])
+    for slot, (case, base, fmt) in enumerate(((r, None, 0), (ra, ra["base_poses"], 1))):
+        want, want_errors, negative = port.transform_track_error(case["raw_poses"], case["lossy_poses"], case["sample_rate"], case["duration"], case["parents"],
+                                                                 case["shell_distances"], port.NORMALIZE_IEEE, base, fmt)
+        rows = matrix[slot * spec.num_samples:(slot + 1) * spec.num_samples, :spec.num_tracks]
+        assert negative and int(got[slot]["flags"]) == ab.ERROR_FLAG_NEGATIVE_SCALE
+        assert clips.bit_equal(rows, want_errors), (name, slot)
+        assert (int(got[slot]["index"]), np.float32(got[slot]["error"]), np.float32(got[slot]["sample_time"])) == (want.index, np.float32(want.error), np.float32(want.sample_time))
+        applied = case["raw_poses"] if base is None else np.stack([port.apply_additive_to_base(fmt, base[s], case["raw_poses"][s]) for s in range(spec.num_samples)])
+        assert float(np.max(np.abs(rows - case["errors"]))) <= error_tolerance(port, applied, case["parents"]), (name, slot)
+
+    d_local = _dev(gpu, r["lossy_poses"])
+    d_object = torch.empty_like(d_local)
+    ctx.local_to_object_space(d_local, d_object, spec.num_samples, spec.num_tracks, _dev(gpu, r["parents"]))
+    torch.cuda.synchronize()
+    got_object = d_object.cpu().numpy()
+    for sample in range(0, spec.num_samples, 5):
+        assert clips.bit_equal(got_object[sample][:, LANES], port.local_to_object_space(r["lossy_poses"][sample], r["parents"], port.NORMALIZE_IEEE)[:, LANES])
+    clipset.release()
+
+
 def test_output_indices_remap(gpu):
     """remap_output (track_error.impl.h:522-532): a raw track the compressed clip does not output is measured with its raw value."""
     port = gpu["port"]
@@ -268,7 +305,10 @@ def test_flags_invalid_skeleton_and_negative_scale(gpu):
     mirrored[2, 5, 8] = -1.0     # rtm::qvv_mul takes its matrix branch for this bone's children
     ctx.local_to_object_space(_dev(gpu, mirrored), d_object, 4, 40, _dev(gpu, parents), d_out_flags=d_flags)
     torch.cuda.synchronize()
-    assert int(d_flags.item()) == ab.ERROR_FLAG_NEGATIVE_SCALE
+    assert int(d_flags.item()) == ab.ERROR_FLAG_NEGATIVE_SCALE        # informational: the matrix branch ran
+    got = d_object.cpu().numpy()
+    for sample in range(4):
+        assert clips.bit_equal(got[sample][:, LANES], gpu["port"].local_to_object_space(mirrored[sample], parents, gpu["port"].NORMALIZE_IEEE)[:, LANES])
 
 
 @pytest.mark.parametrize("name", list(clips.SCALAR_SPECS))
