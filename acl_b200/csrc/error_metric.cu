@@ -247,56 +247,10 @@ namespace aclb200
 			*out = result;
 		}
 
-		__device__ __forceinline__ Qvv<float> stream_of(const Qvv<float2>& q, int stream)
-		{
-			const auto pick = [stream](float2 v) { return stream == 0 ? v.x : v.y; };
-			Qvv<float> out;
-			out.rotation = Quat<float>{ pick(q.rotation.x), pick(q.rotation.y), pick(q.rotation.z), pick(q.rotation.w) };
-			out.translation = Vec3<float>{ pick(q.translation.x), pick(q.translation.y), pick(q.translation.z) };
-			out.scale = Vec3<float>{ pick(q.scale.x), pick(q.scale.y), pick(q.scale.z) };
-			return out;
-		}
-
-		__device__ __forceinline__ void set_stream(Qvv<float2>& q, int stream, const Qvv<float>& value)
-		{
-			const auto put = [stream](float2& v, float a) { if (stream == 0) v.x = a; else v.y = a; };
-			put(q.rotation.x, value.rotation.x); put(q.rotation.y, value.rotation.y); put(q.rotation.z, value.rotation.z); put(q.rotation.w, value.rotation.w);
-			put(q.translation.x, value.translation.x); put(q.translation.y, value.translation.y); put(q.translation.z, value.translation.z);
-			put(q.scale.x, value.scale.x); put(q.scale.y, value.scale.y); put(q.scale.z, value.scale.z);
-		}
-
-		__device__ __forceinline__ bool stream_is_negative(const Qvv<float>& lhs, const Qvv<float>& rhs)
-		{
-			return fminf(lhs.scale.x, rhs.scale.x) < 0.0f || fminf(lhs.scale.y, rhs.scale.y) < 0.0f || fminf(lhs.scale.z, rhs.scale.z) < 0.0f;
-		}
-
-		// replaces the streams of `out` (the positive branch's result) whose operands have a negative scale
-		__device__ __forceinline__ void redo_negative_streams(Qvv<float>& out, const Qvv<float>& lhs, const Qvv<float>& rhs)
-		{
-			qvv_mul_negative_scale(&lhs, &rhs, &out);
-		}
-
-		__device__ __forceinline__ void redo_negative_streams(Qvv<float2>& out, const Qvv<float2>& lhs, const Qvv<float2>& rhs)
-		{
-			#pragma unroll
-			for (int stream = 0; stream < 2; ++stream)
-			{
-				const Qvv<float> l = stream_of(lhs, stream), r = stream_of(rhs, stream);
-				if (stream_is_negative(l, r))
-				{
-					Qvv<float> redone;
-					qvv_mul_negative_scale(&l, &r, &redone);
-					set_stream(out, stream, redone);
-				}
-			}
-		}
-
-		// rtm::qvv_mul(lhs, rhs), external/rtm/includes/rtm/qvvf.h:315-355. `negative` reports that a stream went through the matrix branch
-		// (any min(lhs.scale, rhs.scale) component < 0).
+		// rtm::qvv_mul(lhs, rhs), external/rtm/includes/rtm/qvvf.h:315-355, the positive scale branch (:347-353)
 		template<class V>
-		__device__ __forceinline__ Qvv<V> qvv_mul(const Fp<V>& fp, const Qvv<V>& lhs, const Qvv<V>& rhs, bool& negative)
+		__device__ __forceinline__ Qvv<V> qvv_mul_positive(const Fp<V>& fp, const Qvv<V>& lhs, const Qvv<V>& rhs)
 		{
-			negative = fp.any_negative(lhs.scale.x, rhs.scale.x) || fp.any_negative(lhs.scale.y, rhs.scale.y) || fp.any_negative(lhs.scale.z, rhs.scale.z);
 			Qvv<V> out;
 			out.rotation = quat_mul(fp, lhs.rotation, rhs.rotation);
 			Vec3<V> scaled;
@@ -310,28 +264,23 @@ namespace aclb200
 			out.scale.x = fp.mul(lhs.scale.x, rhs.scale.x);
 			out.scale.y = fp.mul(lhs.scale.y, rhs.scale.y);
 			out.scale.z = fp.mul(lhs.scale.z, rhs.scale.z);
-			if (negative)
-				redo_negative_streams(out, lhs, rhs);
 			return out;
 		}
 
-		// rtm::qvv_normalize(rtm::qvv_mul(local, parent_object)), qvvf.h:426-430: what local_to_object_space does per bone
+		// which branch rtm::qvv_mul takes: vector_any_less_than3(vector_min(lhs.scale, rhs.scale), 0), qvvf.h:317-320 (either stream of a pair)
 		template<class V>
-		__device__ __forceinline__ Qvv<V> qvv_mul_normalize(const Fp<V>& fp, const Qvv<V>& local, const Qvv<V>& parent, bool& negative)
+		__device__ __forceinline__ bool takes_negative_branch(const Fp<V>& fp, const Vec3<V>& lhs_scale, const Vec3<V>& rhs_scale)
 		{
-			Qvv<V> out = qvv_mul(fp, local, parent, negative);
-			out.rotation = quat_normalize(fp, out.rotation);
-			return out;
+			return fp.any_negative(lhs_scale.x, rhs_scale.x) || fp.any_negative(lhs_scale.y, rhs_scale.y) || fp.any_negative(lhs_scale.z, rhs_scale.z);
 		}
 
 		// acl::apply_additive_to_base(format, base, additive), includes/acl/core/additive_utils.h:131-167 (format = additive_clip_format8:
-		// 1 relative, 2 additive0, 3 additive1; transform_add0 / transform_add1 :131-145)
+		// 1 relative = qvv_mul(additive, base), 2 additive0, 3 additive1; transform_add0 / transform_add1 :131-145), positive scales
 		template<class V>
-		__device__ __forceinline__ Qvv<V> apply_additive_to_base(const Fp<V>& fp, uint32_t format, const Qvv<V>& base, const Qvv<V>& additive, bool& negative)
+		__device__ __forceinline__ Qvv<V> apply_additive_to_base_positive(const Fp<V>& fp, uint32_t format, const Qvv<V>& base, const Qvv<V>& additive)
 		{
-			negative = false;
 			if (format == 1)
-				return qvv_mul(fp, additive, base, negative);
+				return qvv_mul_positive(fp, additive, base);
 			Qvv<V> out;
 			out.rotation = quat_mul(fp, additive.rotation, base.rotation);
 			out.translation.x = fp.add(additive.translation.x, base.translation.x);
@@ -436,6 +385,17 @@ namespace aclb200
 			return q;
 		}
 
+		template<class V> __device__ __forceinline__ Qvv<V> make_qvv_pair(const Qvv<float>& q);
+		template<> __device__ __forceinline__ Qvv<float> make_qvv_pair<float>(const Qvv<float>& q) { return q; }
+		template<> __device__ __forceinline__ Qvv<float2> make_qvv_pair<float2>(const Qvv<float>& q)
+		{
+			Qvv<float2> out;
+			out.rotation = Quat<float2>{ make_float2(q.rotation.x, q.rotation.x), make_float2(q.rotation.y, q.rotation.y), make_float2(q.rotation.z, q.rotation.z), make_float2(q.rotation.w, q.rotation.w) };
+			out.translation = Vec3<float2>{ make_float2(q.translation.x, q.translation.x), make_float2(q.translation.y, q.translation.y), make_float2(q.translation.z, q.translation.z) };
+			out.scale = Vec3<float2>{ make_float2(q.scale.x, q.scale.x), make_float2(q.scale.y, q.scale.y), make_float2(q.scale.z, q.scale.z) };
+			return out;
+		}
+
 		// object transforms of a warp's pose in shared memory: [component][bone] planes of V (32 lanes reading 32 different parents hit
 		// different banks; a float2 plane element is one 8 byte access)
 		template<class V>
@@ -468,6 +428,67 @@ namespace aclb200
 			q.scale.y = planes[8 * plane_stride + bone];
 			q.scale.z = planes[9 * plane_stride + bone];
 			return q;
+		}
+
+		// ---- the out of line paths: a bone whose qvv_mul takes the negative scale branch in either stream. They work on the planes in
+		// shared memory, stream by stream on plain floats, so that the packed registers of the fast path never meet a conditional
+		// assignment (a packed value that is conditionally modified gets split into its halves and re-paired with moves) ----
+		template<class V> struct Streams;
+		template<> struct Streams<float> { static constexpr int count = 1; };
+		template<> struct Streams<float2> { static constexpr int count = 2; };
+
+		template<class V>
+		__device__ __forceinline__ Qvv<float> read_stream(const V* planes, uint32_t plane_stride, uint32_t bone, int stream)
+		{
+			const float* words = reinterpret_cast<const float*>(planes);
+			const auto at = [&](uint32_t component) { return words[(size_t(component) * plane_stride + bone) * Streams<V>::count + stream]; };
+			Qvv<float> q;
+			q.rotation = Quat<float>{ at(0), at(1), at(2), at(3) };
+			q.translation = Vec3<float>{ at(4), at(5), at(6) };
+			q.scale = Vec3<float>{ at(7), at(8), at(9) };
+			return q;
+		}
+
+		template<class V>
+		__device__ __forceinline__ void write_stream(V* planes, uint32_t plane_stride, uint32_t bone, int stream, const Qvv<float>& q)
+		{
+			float* words = reinterpret_cast<float*>(planes);
+			const auto put = [&](uint32_t component, float value) { words[(size_t(component) * plane_stride + bone) * Streams<V>::count + stream] = value; };
+			put(0, q.rotation.x); put(1, q.rotation.y); put(2, q.rotation.z); put(3, q.rotation.w);
+			put(4, q.translation.x); put(5, q.translation.y); put(6, q.translation.z);
+			put(7, q.scale.x); put(8, q.scale.y); put(9, q.scale.z);
+		}
+
+		// rtm::qvv_mul on one stream, whichever branch it takes
+		__device__ __forceinline__ Qvv<float> qvv_mul_any(const Qvv<float>& lhs, const Qvv<float>& rhs)
+		{
+			const Fp<float> fp{ 1.0f };
+			if (!takes_negative_branch(fp, lhs.scale, rhs.scale))
+				return qvv_mul_positive(fp, lhs, rhs);
+			Qvv<float> out;
+			qvv_mul_negative_scale(&lhs, &rhs, &out);
+			return out;
+		}
+
+		// planes[bone] = qvv_normalize(qvv_mul(planes[bone] (the local transform), planes[parent])), every stream
+		template<class V>
+		__device__ __noinline__ void object_transform_slow(V* planes, uint32_t plane_stride, uint32_t bone, uint32_t parent)
+		{
+			const Fp<float> fp{ 1.0f };
+			for (int stream = 0; stream < Streams<V>::count; ++stream)
+			{
+				Qvv<float> out = qvv_mul_any(read_stream(planes, plane_stride, bone, stream), read_stream(planes, plane_stride, parent, stream));
+				out.rotation = quat_normalize(fp, out.rotation);
+				write_stream(planes, plane_stride, bone, stream, out);
+			}
+		}
+
+		// planes[bone] = qvv_mul(planes[bone] (the additive transform), base): the `relative` additive format, every stream
+		template<class V>
+		__device__ __noinline__ void apply_relative_slow(V* planes, uint32_t plane_stride, uint32_t bone, const Qvv<float>* base)
+		{
+			for (int stream = 0; stream < Streams<V>::count; ++stream)
+				write_stream(planes, plane_stride, bone, stream, qvv_mul_any(read_stream(planes, plane_stride, bone, stream), *base));
 		}
 
 		// arg max key: larger error wins, then the EARLIER (sample, bone) -- the reference keeps the first maximum it meets walking samples
@@ -595,15 +616,6 @@ namespace aclb200
 						const uint32_t output_index = output_indices != nullptr ? __ldg(output_indices + load_bone) : load_bone;
 						const uint8_t* lossy_bone = output_index != k_invalid_track ? lossy_pose + size_t(output_index) * 48 : raw_pose + size_t(load_bone) * 48;
 						local = make_qvv(raw_local, load_bone48(lossy_bone));
-						if (additive_format != 0)
-						{
-							// apply_additive_to_base on the raw and on the lossy pose before the walk (track_error.impl.h:358-359)
-							const Bone48 base = load_bone48(base_pose + size_t(load_bone) * 48);
-							bool negative = false;
-							local = apply_additive_to_base(fp, additive_format, make_qvv(base, base), local, negative);
-							if (negative && active)
-								pose_flags |= ACLB200_ERROR_FLAG_NEGATIVE_SCALE;
-						}
 					}
 					else
 						local = make_qvv(raw_local);
@@ -614,24 +626,47 @@ namespace aclb200
 						parent = k_invalid_track;
 					}
 
-					// The hierarchy walk of the chunk, in wavefronts: a lane computes once its parent's object transform is in shared memory.
-					// Object transforms go straight to shared memory and come back from there for the measurement: a packed value that lives
-					// in registers across the divergent loop gets split into its halves and re-paired with moves (a third of the instructions
-					// of the first version of this kernel).
-					bool pending = active && parent != k_invalid_track;
-					if (active && parent == k_invalid_track)
-						store_planes(planes, plane_stride, bone, local);			// a root: its object transform is its local transform (:300-301)
+					// The local transform is parked in the bone's own slot of the planes: the object transform will overwrite it. Nothing
+					// packed lives in registers across a branch (see the out of line paths above); a root is done at this point (:300-301).
+					if (active)
+						store_planes(planes, plane_stride, bone, local);
+					if (MODE == 0 && additive_format != 0 && active)
+					{
+						// apply_additive_to_base on the raw and on the lossy pose before the walk (track_error.impl.h:358-359)
+						const Qvv<float> base = make_qvv(load_bone48(base_pose + size_t(bone) * 48));
+						const Qvv<V> base_pair = make_qvv_pair<V>(base);
+						if (additive_format == 1 && takes_negative_branch(fp, local.scale, base_pair.scale))
+						{
+							pose_flags |= ACLB200_ERROR_FLAG_NEGATIVE_SCALE;
+							apply_relative_slow(planes, plane_stride, bone, &base);
+						}
+						else
+							store_planes(planes, plane_stride, bone, apply_additive_to_base_positive(fp, additive_format, base_pair, local));
+					}
 					__syncwarp();
+
+					// the hierarchy walk of the chunk, in wavefronts: a lane computes once its parent's object transform is in shared memory
+					bool pending = active && parent != k_invalid_track;
 					uint32_t done_mask = __ballot_sync(0xFFFFFFFFu, active && !pending);
 					while (__any_sync(0xFFFFFFFFu, pending))
 					{
 						const bool ready = pending && (parent < base || ((done_mask >> (parent - base)) & 1u) != 0);
 						if (ready)
 						{
-							bool negative = false;
-							store_planes(planes, plane_stride, bone, qvv_mul_normalize(fp, local, load_planes(planes, plane_stride, parent), negative));
-							if (negative)
+							const Qvv<V> mine = load_planes(planes, plane_stride, bone);
+							const Qvv<V> above = load_planes(planes, plane_stride, parent);
+							if (takes_negative_branch(fp, mine.scale, above.scale))
+							{
 								pose_flags |= ACLB200_ERROR_FLAG_NEGATIVE_SCALE;
+								object_transform_slow(planes, plane_stride, bone, parent);
+							}
+							else
+							{
+								// rtm::qvv_normalize(rtm::qvv_mul(local, parent_object)), qvvf.h:426-430
+								Qvv<V> object = qvv_mul_positive(fp, mine, above);
+								object.rotation = quat_normalize(fp, object.rotation);
+								store_planes(planes, plane_stride, bone, object);
+							}
 							pending = false;
 						}
 						__syncwarp();
