@@ -356,6 +356,11 @@ namespace aclb200
 			return error;
 		}
 
+		__device__ __forceinline__ void prefetch_l1(const void* address)
+		{
+			asm volatile("prefetch.global.L1 [%0];" :: "l"(address));
+		}
+
 		struct Bone48 { float4 rotation, translation, scale; };
 
 		__device__ __forceinline__ Bone48 load_bone48(const uint8_t* bone)
@@ -559,7 +564,7 @@ namespace aclb200
 
 			for (uint64_t pose = uint64_t(blockIdx.x) * warps_per_block + warp; pose < num_poses; pose += uint64_t(gridDim.x) * warps_per_block)
 			{
-				uint32_t num_tracks, sample = 0, job_slot = 0;
+				uint32_t num_tracks, sample = 0, job_slot = 0, samples_of_job = 0;
 				const uint8_t* raw_pose;
 				const uint8_t* lossy_pose = nullptr;
 				const uint32_t* parents;
@@ -577,6 +582,7 @@ namespace aclb200
 						base_pose = ep.base_poses + (job.first_base_pose + (uint32_t(pose) - job.chunk_first_pose)) * ep.pose_stride;
 					}
 					num_tracks = job.num_tracks;
+					samples_of_job = job.num_samples;
 					sample = uint32_t(pose) - job.chunk_first_pose;
 					job_slot = job.job_index;
 					raw_pose = ep.raw_poses + (job.first_raw_pose + sample) * ep.pose_stride;
@@ -602,6 +608,34 @@ namespace aclb200
 				{
 					const uint32_t bone = base + lane;
 					const bool active = bone < num_tracks;
+					// The next chunk's bones (same pose) are asked for now: with two blocks of eight warps per SM the latency of these loads
+					// is otherwise exposed at the head of every chunk (a fifth of the stall samples of the version without this).
+					if (base + 32 >= num_tracks && MODE == 0)
+					{
+						// last chunk of the pose: the first chunk of the pose this warp takes next (same clip: the raw pose sits a fixed step away)
+						const uint64_t step = uint64_t(gridDim.x) * warps_per_block;
+						if (pose + step < num_poses && lane < num_tracks && output_indices == nullptr)
+						{
+							prefetch_l1(lossy_pose + step * ep.pose_stride + size_t(lane) * 48);
+							prefetch_l1(lossy_pose + step * ep.pose_stride + size_t(lane) * 48 + 32);
+							if (sample + step < samples_of_job)
+							{
+								prefetch_l1(raw_pose + step * ep.pose_stride + size_t(lane) * 48);
+								prefetch_l1(raw_pose + step * ep.pose_stride + size_t(lane) * 48 + 32);
+							}
+						}
+					}
+					else if (base + 32 + lane < num_tracks)
+					{
+						prefetch_l1(raw_pose + size_t(base + 32 + lane) * 48);
+						prefetch_l1(raw_pose + size_t(base + 32 + lane) * 48 + 32);
+						if (MODE == 0 && output_indices == nullptr)
+						{
+							prefetch_l1(lossy_pose + size_t(base + 32 + lane) * 48);
+							prefetch_l1(lossy_pose + size_t(base + 32 + lane) * 48 + 32);
+						}
+					}
+
 					// Lanes past the last bone load the last bone again (their results are never stored): no value of the loop below depends
 					// on a branch, which keeps the packed pairs in aligned register pairs from the load to the arithmetic.
 					const uint32_t load_bone = active ? bone : num_tracks - 1;
