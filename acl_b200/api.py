@@ -130,6 +130,7 @@ def _lib():
         l.aclb200_copy_to_host.argtypes = [vp, vp, vp, C.c_size_t]
         l.aclb200_calculate_compression_error.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp, C.POINTER(Options), vp, vp, vp]
         l.aclb200_set_error_chunk_bytes.argtypes = [vp, u64]
+        l.aclb200_decompress_all_samples.argtypes = [vp, vp, vp, u32, C.POINTER(Options), vp, vp]
         l.aclb200_local_to_object_space.argtypes = [vp, vp, vp, u64, u32, u64, vp, vp, vp]
         l.aclb200_launch_count.argtypes = [vp]
         l.aclb200_launch_count.restype = u64
@@ -147,6 +148,7 @@ def exported_symbols() -> list[str]:
         "aclb200_debug_seek", "aclb200_debug_unpack", "aclb200_debug_set_trace", "aclb200_launch_count",
         "aclb200_device_malloc", "aclb200_device_free", "aclb200_copy_to_device", "aclb200_copy_to_host",
         "aclb200_calculate_compression_error", "aclb200_set_error_chunk_bytes", "aclb200_local_to_object_space",
+        "aclb200_decompress_all_samples",
     ]
 
 
@@ -301,6 +303,12 @@ class Context:
             self._handle, clipset._handle, jobs.ctypes.data, jobs.shape[0], _device_ptr(d_raw_poses), _device_ptr(d_parent_indices),
             _device_ptr(d_shell_distances), _device_ptr(d_output_indices), _device_ptr(d_base_poses), C.byref(options), _device_ptr(d_out_errors),
             _device_ptr(d_out_error_matrix), _stream_ptr(stream)))
+
+    def decompress_all_samples(self, clipset: ClipSet, jobs: np.ndarray, options: Options, d_out, stream=None) -> None:
+        jobs = np.ascontiguousarray(jobs)
+        assert jobs.dtype == ERROR_JOB_DTYPE
+        self._check(_lib().aclb200_decompress_all_samples(self._handle, clipset._handle, jobs.ctypes.data, jobs.shape[0], C.byref(options),
+                                                          _device_ptr(d_out), _stream_ptr(stream)))
 
     def set_error_chunk_bytes(self, num_bytes: int) -> None:
         self._check(_lib().aclb200_set_error_chunk_bytes(self._handle, num_bytes))

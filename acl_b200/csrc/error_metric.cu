@@ -20,6 +20,7 @@
 #include "context.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 #include <vector>
@@ -548,8 +549,10 @@ namespace aclb200
 			float    one;
 		};
 
-		template<int MODE>
-		__global__ void __launch_bounds__(256) object_space_kernel(ErrorParams ep, ObjectSpaceParams op)
+		// THREADS / MIN_BLOCKS: 256 x 2 (eight poses per block) or 192 x 3 (six poses per block, a tighter register budget): whichever keeps
+		// more warps resident for the skeleton at hand (launch_object_space)
+		template<int MODE, int THREADS = 256, int MIN_BLOCKS = 2>
+		__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) object_space_kernel(ErrorParams ep, ObjectSpaceParams op)
 		{
 			using V = typename std::conditional<MODE == 0, float2, float>::type;
 			extern __shared__ __align__(16) uint8_t object_plane_bytes[];
@@ -858,6 +861,8 @@ namespace aclb200
 		cudaError_t error = cudaFuncSetAttribute(object_space_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin_limit);
 		if (error == cudaSuccess)
 			error = cudaFuncSetAttribute(object_space_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin_limit);
+		if (error == cudaSuccess)
+			error = cudaFuncSetAttribute(object_space_kernel<0, 192, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin_limit);
 		return error;
 	}
 }
@@ -993,9 +998,14 @@ extern "C"
 		}
 
 		const uint32_t plane_stride = plane_stride_for(widest);
-		const uint32_t warps = is_transform ? warps_for(plane_stride, 2, context->max_dynamic_smem) : 8u;
+		uint32_t warps = is_transform ? warps_for(plane_stride, 2, context->max_dynamic_smem) : 8u;
 		if (warps == 0)
 			return set_error(context, ACLB200_ERR_UNSUPPORTED, "calculate_compression_error: the skeleton's object transforms do not fit in shared memory");
+		// ACLB200_ERROR_WARPS=6: three blocks of six warps per SM instead of two of eight (tuning; needs 3 x 6 poses of planes per SM)
+		static const char* const override_warps = std::getenv("ACLB200_ERROR_WARPS");
+		if (is_transform && override_warps != nullptr && override_warps[0] == '6' && warps == 8
+			&& 3 * 6 * size_t(2) * k_object_components * plane_stride * sizeof(float) + 3 * 1024 <= size_t(228) * 1024)
+			warps = 6;
 
 		// chunks: runs of jobs of one group whose decoded poses fit the scratch budget (one job at least)
 		const uint64_t budget_poses = std::max<uint64_t>(1, context->error_chunk_bytes / std::max<uint64_t>(stride, 1));
@@ -1099,7 +1109,10 @@ extern "C"
 				const uint32_t blocks_needed = (chunk.num_poses + warps - 1) / warps;
 				const uint32_t blocks = std::min<uint32_t>(blocks_needed, uint32_t(context->num_sms) * 32);
 				const size_t smem = size_t(warps) * 2 * k_object_components * plane_stride * sizeof(float);
-				object_space_kernel<0><<<blocks, warps * 32, smem, cuda_stream>>>(p, ObjectSpaceParams{});
+				if (warps == 6)
+					object_space_kernel<0, 192, 3><<<blocks, warps * 32, smem, cuda_stream>>>(p, ObjectSpaceParams{});
+				else
+					object_space_kernel<0><<<blocks, warps * 32, smem, cuda_stream>>>(p, ObjectSpaceParams{});
 			}
 			else
 			{
@@ -1117,6 +1130,69 @@ extern "C"
 		if (error == cudaSuccess)
 			context->launch_count++;
 		return check_cuda(context, error, "calculate_compression_error");
+	}
+
+	aclb200_status aclb200_decompress_all_samples(aclb200_context* context, const aclb200_clipset* clipset, const aclb200_error_job* jobs,
+		uint32_t num_jobs, const aclb200_options* options, void* d_out, void* stream)
+	{
+		if (context == nullptr || clipset == nullptr || options == nullptr)
+			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "null context / clipset / options");
+		if (num_jobs == 0)
+			return ACLB200_OK;
+		if (jobs == nullptr || d_out == nullptr)
+			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "decompress_all_samples: null jobs / output");
+		if (options->d_request_policies != nullptr)
+			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "decompress_all_samples builds its own requests: d_request_policies does not apply");
+
+		// the requests of every job, back to back: sample i of a clip at min(i / sample_rate, duration) (convert.impl.h:168)
+		std::vector<ErrorJobDev> ordered(num_jobs);
+		uint64_t total_poses = 0;
+		for (uint32_t index = 0; index < num_jobs; ++index)
+		{
+			if (jobs[index].clip >= clipset->info.num_clips)
+				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "decompress_all_samples: job names a clip outside the clip set");
+			ErrorJobDev dev = {};
+			dev.clip = jobs[index].clip;
+			dev.num_samples = jobs[index].num_samples;
+			dev.sample_rate = jobs[index].sample_rate;
+			dev.duration = jobs[index].duration;
+			dev.chunk_first_pose = uint32_t(total_poses);
+			dev.job_index = index;
+			ordered[index] = dev;
+			total_poses += jobs[index].num_samples;
+		}
+		if (total_poses == 0)
+			return ACLB200_OK;
+		if (total_poses > 0x7FFFFFFFull)
+			return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "decompress_all_samples: more than 2^31 poses in one call");
+
+		const size_t jobs_bytes = align_up(sizeof(ErrorJobDev) * ordered.size(), 256);
+		const size_t requests_bytes = align_up(sizeof(aclb200_request) * size_t(total_poses), 256);
+		const size_t pose_jobs_bytes = align_up(sizeof(uint32_t) * size_t(total_poses), 256);
+		cudaSetDevice(context->device);
+		const aclb200_status grown = grow_scratch(context, jobs_bytes + requests_bytes + pose_jobs_bytes);
+		if (grown != ACLB200_OK)
+			return grown;
+		uint8_t* scratch = static_cast<uint8_t*>(context->d_error_scratch);
+		cudaStream_t cuda_stream = static_cast<cudaStream_t>(stream);
+		cudaError_t error = cudaMemcpyAsync(scratch, ordered.data(), sizeof(ErrorJobDev) * ordered.size(), cudaMemcpyHostToDevice, cuda_stream);
+		if (error != cudaSuccess)
+			return check_cuda(context, error, "decompress_all_samples: job upload");
+
+		ErrorParams p = {};
+		p.jobs = reinterpret_cast<const ErrorJobDev*>(scratch);
+		p.num_jobs = num_jobs;
+		p.num_poses = uint32_t(total_poses);
+		p.requests = reinterpret_cast<aclb200_request*>(scratch + jobs_bytes);
+		p.pose_jobs = reinterpret_cast<uint32_t*>(scratch + jobs_bytes + requests_bytes);
+		build_error_requests_kernel<<<(p.num_poses + 255) / 256, 256, 0, cuda_stream>>>(p);
+		error = cudaGetLastError();
+		if (error != cudaSuccess)
+			return check_cuda(context, error, "decompress_all_samples: request setup");
+		context->launch_count++;
+		return clipset->info.track_type == ACLB200_TRACK_QVVF
+			? aclb200_decompress_tracks(context, clipset, p.requests, p.num_poses, options, d_out, stream)
+			: aclb200_scalar_decompress_tracks(context, clipset, p.requests, p.num_poses, options, d_out, stream);
 	}
 
 	aclb200_status aclb200_set_error_chunk_bytes(aclb200_context* context, uint64_t bytes)

@@ -296,6 +296,15 @@ ACLB200_API aclb200_status aclb200_calculate_compression_error(aclb200_context* 
 	const uint32_t* d_output_indices, const void* d_base_poses, const aclb200_options* options, aclb200_track_error* d_out_errors,
 	float* d_out_error_matrix, void* stream);
 
+/* The sampling loop of acl::convert_track_list(allocator, const compressed_tracks&, track_array&) (compression/convert.h,
+ * compression/impl/convert.impl.h:146-232) and of the error measurement above: EVERY sample of every listed clip in one launch sequence.
+ * Job j contributes num_samples poses, sample i sought at min(i / sample_rate, duration) with options->rounding_policy (the reference
+ * uses `nearest` "to land directly on a sample") and decoded like aclb200_decompress_tracks / aclb200_scalar_decompress_tracks would:
+ * the poses of the jobs follow one another in d_out (pose stride and layout from `options`). Only clip, num_samples, sample_rate and
+ * duration of a job are read. jobs is a HOST array; asynchronous on `stream`; uses scratch owned by the context. */
+ACLB200_API aclb200_status aclb200_decompress_all_samples(aclb200_context* context, const aclb200_clipset* clipset, const aclb200_error_job* jobs,
+	uint32_t num_jobs, const aclb200_options* options, void* d_out, void* stream);
+
 /* Decoded poses held per chunk of clips by aclb200_calculate_compression_error (default 512 MiB). */
 ACLB200_API aclb200_status aclb200_set_error_chunk_bytes(aclb200_context* context, uint64_t bytes);
 

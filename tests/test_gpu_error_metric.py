@@ -357,3 +357,28 @@ def test_rejects_what_it_cannot_measure(gpu):
     got, _ = _measure(gpu, clipset, _jobs(gpu, [dict(good, num_samples=0)]), raw, parents, shells, ab.Options())
     assert (int(got[0]["index"]), float(got[0]["error"]), float(got[0]["sample_time"])) == (0xFFFFFFFF, 0.0, 0.0)
     clipset.release()
+
+
+def test_decompress_all_samples_is_the_reference_sampling_loop(gpu):
+    """aclb200_decompress_all_samples == the loop of convert_track_list / calculate_compression_error (convert.impl.h:164-171,
+    track_error.impl.h:337-339): every sample of several clips in one call, bit for bit what the reference decoded sample by sample."""
+    torch, ab, ctx = gpu["torch"], gpu["ab"], gpu["ctx"]
+    names = ["mixed_scale", "c1_30bones", "ragged_17", "looping", "one_sample"]
+    clipset = ctx.upload([clips.load_blob(n) for n in names], check_hash=True)
+    cases = [_reference_case(n, 1) for n in names]
+    order = [2, 0, 4, 3, 1, 0]
+    rows = [dict(clip=c, num_samples=clips.TRANSFORM_SPECS[names[c]].num_samples, sample_rate=cases[c]["sample_rate"], duration=cases[c]["duration"]) for c in order]
+    total = sum(r["num_samples"] for r in rows)
+    options = _options(gpu, 1)
+    options.rounding_policy = ab.ROUND_NEAREST
+    d_out = torch.full((total, clipset.max_tracks, 12), float("nan"), dtype=torch.float32, device="cuda")
+    ctx.decompress_all_samples(clipset, _jobs(gpu, rows), options, d_out)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    row = 0
+    for c in order:
+        spec = clips.TRANSFORM_SPECS[names[c]]
+        assert cases[c]["rounding"] == ab.ROUND_NEAREST
+        assert clips.bit_equal(got[row:row + spec.num_samples, :spec.num_tracks][..., LANES], cases[c]["lossy_poses"][..., LANES]), names[c]
+        row += spec.num_samples
+    clipset.release()
