@@ -31,7 +31,7 @@ struct aclb200_context
 	// aclb200_calculate_compression_error (error_metric.cu): job table, arg max accumulators, requests and the decoded poses of one chunk
 	void* d_error_scratch = nullptr;
 	size_t error_scratch_bytes = 0;
-	uint64_t error_chunk_bytes = 512ull << 20;	// decoded poses per chunk (aclb200_set_error_chunk_bytes)
+	uint64_t error_chunk_bytes = 1024ull << 20;	// decoded poses per chunk (aclb200_set_error_chunk_bytes)
 
 	// aclb200_debug_set_trace
 	unsigned long long* d_trace = nullptr;

@@ -357,11 +357,6 @@ namespace aclb200
 			return error;
 		}
 
-		__device__ __forceinline__ void prefetch_l1(const void* address)
-		{
-			asm volatile("prefetch.global.L1 [%0];" :: "l"(address));
-		}
-
 		struct Bone48 { float4 rotation, translation, scale; };
 
 		__device__ __forceinline__ Bone48 load_bone48(const uint8_t* bone)
@@ -549,10 +544,8 @@ namespace aclb200
 			float    one;
 		};
 
-		// THREADS / MIN_BLOCKS: 256 x 2 (eight poses per block) or 192 x 3 (six poses per block, a tighter register budget): whichever keeps
-		// more warps resident for the skeleton at hand (launch_object_space)
-		template<int MODE, int THREADS = 256, int MIN_BLOCKS = 2>
-		__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) object_space_kernel(ErrorParams ep, ObjectSpaceParams op)
+		template<int MODE>
+		__global__ void __launch_bounds__(256, 2) object_space_kernel(ErrorParams ep, ObjectSpaceParams op)
 		{
 			using V = typename std::conditional<MODE == 0, float2, float>::type;
 			extern __shared__ __align__(16) uint8_t object_plane_bytes[];
@@ -567,7 +560,7 @@ namespace aclb200
 
 			for (uint64_t pose = uint64_t(blockIdx.x) * warps_per_block + warp; pose < num_poses; pose += uint64_t(gridDim.x) * warps_per_block)
 			{
-				uint32_t num_tracks, sample = 0, job_slot = 0, samples_of_job = 0;
+				uint32_t num_tracks, sample = 0, job_slot = 0;
 				const uint8_t* raw_pose;
 				const uint8_t* lossy_pose = nullptr;
 				const uint32_t* parents;
@@ -585,7 +578,6 @@ namespace aclb200
 						base_pose = ep.base_poses + (job.first_base_pose + (uint32_t(pose) - job.chunk_first_pose)) * ep.pose_stride;
 					}
 					num_tracks = job.num_tracks;
-					samples_of_job = job.num_samples;
 					sample = uint32_t(pose) - job.chunk_first_pose;
 					job_slot = job.job_index;
 					raw_pose = ep.raw_poses + (job.first_raw_pose + sample) * ep.pose_stride;
@@ -611,34 +603,6 @@ namespace aclb200
 				{
 					const uint32_t bone = base + lane;
 					const bool active = bone < num_tracks;
-					// The next chunk's bones (same pose) are asked for now: with two blocks of eight warps per SM the latency of these loads
-					// is otherwise exposed at the head of every chunk (a fifth of the stall samples of the version without this).
-					if (base + 32 >= num_tracks && MODE == 0)
-					{
-						// last chunk of the pose: the first chunk of the pose this warp takes next (same clip: the raw pose sits a fixed step away)
-						const uint64_t step = uint64_t(gridDim.x) * warps_per_block;
-						if (pose + step < num_poses && lane < num_tracks && output_indices == nullptr)
-						{
-							prefetch_l1(lossy_pose + step * ep.pose_stride + size_t(lane) * 48);
-							prefetch_l1(lossy_pose + step * ep.pose_stride + size_t(lane) * 48 + 32);
-							if (sample + step < samples_of_job)
-							{
-								prefetch_l1(raw_pose + step * ep.pose_stride + size_t(lane) * 48);
-								prefetch_l1(raw_pose + step * ep.pose_stride + size_t(lane) * 48 + 32);
-							}
-						}
-					}
-					else if (base + 32 + lane < num_tracks)
-					{
-						prefetch_l1(raw_pose + size_t(base + 32 + lane) * 48);
-						prefetch_l1(raw_pose + size_t(base + 32 + lane) * 48 + 32);
-						if (MODE == 0 && output_indices == nullptr)
-						{
-							prefetch_l1(lossy_pose + size_t(base + 32 + lane) * 48);
-							prefetch_l1(lossy_pose + size_t(base + 32 + lane) * 48 + 32);
-						}
-					}
-
 					// Lanes past the last bone load the last bone again (their results are never stored): no value of the loop below depends
 					// on a branch, which keeps the packed pairs in aligned register pairs from the load to the arithmetic.
 					const uint32_t load_bone = active ? bone : num_tracks - 1;
@@ -861,8 +825,6 @@ namespace aclb200
 		cudaError_t error = cudaFuncSetAttribute(object_space_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin_limit);
 		if (error == cudaSuccess)
 			error = cudaFuncSetAttribute(object_space_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin_limit);
-		if (error == cudaSuccess)
-			error = cudaFuncSetAttribute(object_space_kernel<0, 192, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin_limit);
 		return error;
 	}
 }
@@ -998,14 +960,9 @@ extern "C"
 		}
 
 		const uint32_t plane_stride = plane_stride_for(widest);
-		uint32_t warps = is_transform ? warps_for(plane_stride, 2, context->max_dynamic_smem) : 8u;
+		const uint32_t warps = is_transform ? warps_for(plane_stride, 2, context->max_dynamic_smem) : 8u;
 		if (warps == 0)
 			return set_error(context, ACLB200_ERR_UNSUPPORTED, "calculate_compression_error: the skeleton's object transforms do not fit in shared memory");
-		// ACLB200_ERROR_WARPS=6: three blocks of six warps per SM instead of two of eight (tuning; needs 3 x 6 poses of planes per SM)
-		static const char* const override_warps = std::getenv("ACLB200_ERROR_WARPS");
-		if (is_transform && override_warps != nullptr && override_warps[0] == '6' && warps == 8
-			&& 3 * 6 * size_t(2) * k_object_components * plane_stride * sizeof(float) + 3 * 1024 <= size_t(228) * 1024)
-			warps = 6;
 
 		// chunks: runs of jobs of one group whose decoded poses fit the scratch budget (one job at least)
 		const uint64_t budget_poses = std::max<uint64_t>(1, context->error_chunk_bytes / std::max<uint64_t>(stride, 1));
@@ -1109,10 +1066,7 @@ extern "C"
 				const uint32_t blocks_needed = (chunk.num_poses + warps - 1) / warps;
 				const uint32_t blocks = std::min<uint32_t>(blocks_needed, uint32_t(context->num_sms) * 32);
 				const size_t smem = size_t(warps) * 2 * k_object_components * plane_stride * sizeof(float);
-				if (warps == 6)
-					object_space_kernel<0, 192, 3><<<blocks, warps * 32, smem, cuda_stream>>>(p, ObjectSpaceParams{});
-				else
-					object_space_kernel<0><<<blocks, warps * 32, smem, cuda_stream>>>(p, ObjectSpaceParams{});
+				object_space_kernel<0><<<blocks, warps * 32, smem, cuda_stream>>>(p, ObjectSpaceParams{});
 			}
 			else
 			{

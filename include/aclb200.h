@@ -305,7 +305,7 @@ ACLB200_API aclb200_status aclb200_calculate_compression_error(aclb200_context* 
 ACLB200_API aclb200_status aclb200_decompress_all_samples(aclb200_context* context, const aclb200_clipset* clipset, const aclb200_error_job* jobs,
 	uint32_t num_jobs, const aclb200_options* options, void* d_out, void* stream);
 
-/* Decoded poses held per chunk of clips by aclb200_calculate_compression_error (default 512 MiB). */
+/* Decoded poses held per chunk of clips by aclb200_calculate_compression_error (default 1 GiB). */
 ACLB200_API aclb200_status aclb200_set_error_chunk_bytes(aclb200_context* context, uint64_t bytes);
 
 /* Replaces qvvf_transform_error_metric::local_to_object_space (compression/transform_error_metrics.h:289-310: obj[i] =

@@ -141,7 +141,7 @@ def test_compression_error_many_clips_ragged_chunked(gpu):
         pose_offset += spec.num_samples
     jobs = _jobs(gpu, rows)
     raw = np.concatenate(raw_rows)
-    for chunk_bytes in (512 << 20, 100 * max_tracks * 48):
+    for chunk_bytes in (1024 << 20, 100 * max_tracks * 48):
         ctx.set_error_chunk_bytes(chunk_bytes)
         got, matrix = _measure(gpu, clipset, jobs, raw, np.concatenate(parents), np.concatenate(shells), _options(gpu, 1))
         row = 0
@@ -150,7 +150,7 @@ def test_compression_error_many_clips_ragged_chunked(gpu):
             _check_against(gpu, got[slot], matrix[row:row + spec.num_samples, :spec.num_tracks], r["raw_poses"], r["lossy_poses"], r["sample_rate"],
                            r["duration"], r["parents"], r["shell_distances"], r, (names[clip], slot, chunk_bytes))
             row += spec.num_samples
-    ctx.set_error_chunk_bytes(512 << 20)
+    ctx.set_error_chunk_bytes(1024 << 20)
     clipset.release()
 
 

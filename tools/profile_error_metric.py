@@ -13,7 +13,7 @@ from oracle import ref
 
 num_clips = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 calls = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-chunk_mb = int(sys.argv[3]) if len(sys.argv) > 3 else 512
+chunk_mb = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
 spec = ref.TransformSpec(num_tracks=100, num_samples=60, seed=2000)
 buffer, offsets, sizes = ref.compress_transform_batch(spec, num_clips, num_threads=ref.usable_threads())
 raw, parents, shells = ref.sample_raw_transform_batch(spec, num_clips)
