@@ -31,7 +31,8 @@ SEEK_STATE_DTYPE = np.dtype([
 # numpy views of aclb200_error_job / aclb200_track_error
 ERROR_JOB_DTYPE = np.dtype([("clip", np.uint32), ("num_samples", np.uint32), ("sample_rate", np.float32), ("duration", np.float32),
                             ("num_tracks", np.uint32), ("skeleton_offset", np.uint32), ("first_raw_pose", np.uint64),
-                            ("additive_format", np.uint32), ("reserved", np.uint32), ("first_base_pose", np.uint64)])
+                            ("additive_format", np.uint32), ("error_metric", np.uint32), ("first_base_pose", np.uint64)])
+METRIC_QVVF, METRIC_QVVF_MATRIX3X4F = 0, 1
 ADDITIVE_NONE, ADDITIVE_RELATIVE, ADDITIVE_ADDITIVE0, ADDITIVE_ADDITIVE1 = 0, 1, 2, 3
 TRACK_ERROR_DTYPE = np.dtype([("index", np.uint32), ("error", np.float32), ("sample_time", np.float32), ("flags", np.uint32)])
 ERROR_FLAG_NEGATIVE_SCALE, ERROR_FLAG_INVALID_SKELETON = 1, 2

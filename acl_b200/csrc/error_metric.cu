@@ -336,6 +336,67 @@ namespace aclb200
 			}
 		}
 
+		// ---- qvvf_matrix3x4f_transform_error_metric (transform_error_metrics.h:389-464): the same walk on 3x4 matrices. Every operation is an
+		// IEEE mul / add / sqrt: this metric is bit-identical to the reference on any CPU ----
+		template<class V> struct Mat34 { V m[4][3]; };		// rows: x_axis, y_axis, z_axis, w_axis (translation)
+
+		// rtm::matrix_from_qvv, matrix3x4f.h:134-159 (convert_transforms :397-413)
+		template<class V>
+		__device__ __forceinline__ Mat34<V> matrix_from_qvv(const Fp<V>& fp, const Qvv<V>& q)
+		{
+			const V x2 = fp.add(q.rotation.x, q.rotation.x), y2 = fp.add(q.rotation.y, q.rotation.y), z2 = fp.add(q.rotation.z, q.rotation.z);
+			const V xx = fp.mul(q.rotation.x, x2), xy = fp.mul(q.rotation.x, y2), xz = fp.mul(q.rotation.x, z2);
+			const V yy = fp.mul(q.rotation.y, y2), yz = fp.mul(q.rotation.y, z2), zz = fp.mul(q.rotation.z, z2);
+			const V wx = fp.mul(q.rotation.w, x2), wy = fp.mul(q.rotation.w, y2), wz = fp.mul(q.rotation.w, z2);
+			const V one = fp.splat(1.0f);
+			Mat34<V> out;
+			out.m[0][0] = fp.mul(fp.sub(one, fp.add(yy, zz)), q.scale.x);	out.m[0][1] = fp.mul(fp.add(xy, wz), q.scale.x);				out.m[0][2] = fp.mul(fp.sub(xz, wy), q.scale.x);
+			out.m[1][0] = fp.mul(fp.sub(xy, wz), q.scale.y);				out.m[1][1] = fp.mul(fp.sub(one, fp.add(xx, zz)), q.scale.y);	out.m[1][2] = fp.mul(fp.add(yz, wx), q.scale.y);
+			out.m[2][0] = fp.mul(fp.add(xz, wy), q.scale.z);				out.m[2][1] = fp.mul(fp.sub(yz, wx), q.scale.z);				out.m[2][2] = fp.mul(fp.sub(one, fp.add(xx, yy)), q.scale.z);
+			out.m[3][0] = q.translation.x;									out.m[3][1] = q.translation.y;									out.m[3][2] = q.translation.z;
+			return out;
+		}
+
+		// rtm::matrix_mul(lhs, rhs), matrix3x4f.h:298-321 (local_to_object_space :415-436)
+		template<class V>
+		__device__ __forceinline__ Mat34<V> matrix_mul(const Fp<V>& fp, const Mat34<V>& l, const Mat34<V>& r)
+		{
+			Mat34<V> out;
+			#pragma unroll
+			for (int row = 0; row < 4; ++row)
+				#pragma unroll
+				for (int c = 0; c < 3; ++c)
+				{
+					V tmp = fp.mul(l.m[row][0], r.m[0][c]);
+					tmp = fp.add(fp.mul(l.m[row][1], r.m[1][c]), tmp);
+					tmp = fp.add(fp.mul(l.m[row][2], r.m[2][c]), tmp);
+					out.m[row][c] = row == 3 ? fp.add(r.m[3][c], tmp) : tmp;
+				}
+			return out;
+		}
+
+		template<class V>
+		__device__ __forceinline__ void store_matrix_planes(V* planes, uint32_t plane_stride, uint32_t bone, const Mat34<V>& q)
+		{
+			#pragma unroll
+			for (int row = 0; row < 4; ++row)
+				#pragma unroll
+				for (int c = 0; c < 3; ++c)
+					planes[(row * 3 + c) * plane_stride + bone] = q.m[row][c];
+		}
+
+		template<class V>
+		__device__ __forceinline__ Mat34<V> load_matrix_planes(const V* planes, uint32_t plane_stride, uint32_t bone)
+		{
+			Mat34<V> q;
+			#pragma unroll
+			for (int row = 0; row < 4; ++row)
+				#pragma unroll
+				for (int c = 0; c < 3; ++c)
+					q.m[row][c] = planes[(row * 3 + c) * plane_stride + bone];
+			return q;
+		}
+
 		__device__ __forceinline__ float max_ss(float a, float b) { return a > b ? a : b; }		// _mm_max_ss: the second operand when unordered
 
 		// qvvf_transform_error_metric::calculate_error, transform_error_metrics.h:335-358: per shell point
@@ -351,6 +412,25 @@ namespace aclb200
 				const float dx = __fsub_rn(points[axis].x.x, points[axis].x.y);
 				const float dy = __fsub_rn(points[axis].y.x, points[axis].y.y);
 				const float dz = __fsub_rn(points[axis].z.x, points[axis].z.y);
+				const float axis_error = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+				error = axis == 0 ? axis_error : max_ss(error, axis_error);
+			}
+			return error;
+		}
+
+		// calculate_error of the matrix metric (:438-463): rtm::matrix_mul_point3 (matrix3x4f.h:326-336) of the shell points (d, 0, 0), (0, d, 0),
+		// (0, 0, d) comes down to d * axis + w_axis once the terms that multiply a zero component are dropped (same argument as shell_points)
+		__device__ __forceinline__ float matrix_calculate_error(const Fp<float2>& fp, const Mat34<float2>& object, float shell_distance)
+		{
+			const float2 d = fp.splat(shell_distance);
+			float error = 0.0f;
+			#pragma unroll
+			for (int axis = 0; axis < 3; ++axis)
+			{
+				const float2 x = fp.add(fp.mul(d, object.m[axis][0]), object.m[3][0]);
+				const float2 y = fp.add(fp.mul(d, object.m[axis][1]), object.m[3][1]);
+				const float2 z = fp.add(fp.mul(d, object.m[axis][2]), object.m[3][2]);
+				const float dx = __fsub_rn(x.x, x.y), dy = __fsub_rn(y.x, y.y), dz = __fsub_rn(z.x, z.y);
 				const float axis_error = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
 				error = axis == 0 ? axis_error : max_ss(error, axis_error);
 			}
@@ -544,7 +624,8 @@ namespace aclb200
 			float    one;
 		};
 
-		template<int MODE>
+		// METRIC (MODE 0 only): 0 = qvvf_transform_error_metric, 1 = qvvf_matrix3x4f_transform_error_metric
+		template<int MODE, int METRIC = 0>
 		__global__ void __launch_bounds__(256, 2) object_space_kernel(ErrorParams ep, ObjectSpaceParams op)
 		{
 			using V = typename std::conditional<MODE == 0, float2, float>::type;
@@ -553,7 +634,8 @@ namespace aclb200
 			const uint32_t warp = threadIdx.x >> 5;
 			const uint32_t warps_per_block = blockDim.x >> 5;
 			const uint32_t plane_stride = MODE == 0 ? ep.plane_stride : op.plane_stride;
-			V* planes = reinterpret_cast<V*>(object_plane_bytes) + size_t(warp) * k_object_components * plane_stride;
+			constexpr uint32_t k_components = METRIC == 1 ? 12u : k_object_components;
+			V* planes = reinterpret_cast<V*>(object_plane_bytes) + size_t(warp) * k_components * plane_stride;
 			const uint64_t num_poses = MODE == 0 ? uint64_t(ep.num_poses) : op.num_poses;
 			Fp<V> fp;
 			fp.one = MODE == 0 ? ep.one : op.one;
@@ -630,8 +712,13 @@ namespace aclb200
 					// The local transform is parked in the bone's own slot of the planes: the object transform will overwrite it. Nothing
 					// packed lives in registers across a branch (see the out of line paths above); a root is done at this point (:300-301).
 					if (active)
-						store_planes(planes, plane_stride, bone, local);
-					if (MODE == 0 && additive_format != 0 && active)
+					{
+						if constexpr (METRIC == 1)
+							store_matrix_planes(planes, plane_stride, bone, matrix_from_qvv(fp, local));		// convert_transforms
+						else
+							store_planes(planes, plane_stride, bone, local);
+					}
+					if (MODE == 0 && METRIC == 0 && additive_format != 0 && active)
 					{
 						// apply_additive_to_base on the raw and on the lossy pose before the walk (track_error.impl.h:358-359)
 						const Qvv<float> base = make_qvv(load_bone48(base_pose + size_t(bone) * 48));
@@ -654,19 +741,24 @@ namespace aclb200
 						const bool ready = pending && (parent < base || ((done_mask >> (parent - base)) & 1u) != 0);
 						if (ready)
 						{
-							const Qvv<V> mine = load_planes(planes, plane_stride, bone);
-							const Qvv<V> above = load_planes(planes, plane_stride, parent);
-							if (takes_negative_branch(fp, mine.scale, above.scale))
-							{
-								pose_flags |= ACLB200_ERROR_FLAG_NEGATIVE_SCALE;
-								object_transform_slow(planes, plane_stride, bone, parent);
-							}
+							if constexpr (METRIC == 1)
+								store_matrix_planes(planes, plane_stride, bone, matrix_mul(fp, load_matrix_planes(planes, plane_stride, bone), load_matrix_planes(planes, plane_stride, parent)));
 							else
 							{
-								// rtm::qvv_normalize(rtm::qvv_mul(local, parent_object)), qvvf.h:426-430
-								Qvv<V> object = qvv_mul_positive(fp, mine, above);
-								object.rotation = quat_normalize(fp, object.rotation);
-								store_planes(planes, plane_stride, bone, object);
+								const Qvv<V> mine = load_planes(planes, plane_stride, bone);
+								const Qvv<V> above = load_planes(planes, plane_stride, parent);
+								if (takes_negative_branch(fp, mine.scale, above.scale))
+								{
+									pose_flags |= ACLB200_ERROR_FLAG_NEGATIVE_SCALE;
+									object_transform_slow(planes, plane_stride, bone, parent);
+								}
+								else
+								{
+									// rtm::qvv_normalize(rtm::qvv_mul(local, parent_object)), qvvf.h:426-430
+									Qvv<V> object = qvv_mul_positive(fp, mine, above);
+									object.rotation = quat_normalize(fp, object.rotation);
+									store_planes(planes, plane_stride, bone, object);
+								}
 							}
 							pending = false;
 						}
@@ -677,10 +769,13 @@ namespace aclb200
 					// every lane of the chunk at once: the measurement (or the store) needs nothing but the lane's own object transform
 					if (active)
 					{
-						const Qvv<V> object = load_planes(planes, plane_stride, bone);
 						if constexpr (MODE == 0)
 						{
-							const float error = calculate_error(fp, object, shell);
+							float error;
+							if constexpr (METRIC == 1)
+								error = matrix_calculate_error(fp, load_matrix_planes(planes, plane_stride, bone), shell);
+							else
+								error = calculate_error(fp, load_planes(planes, plane_stride, bone), shell);
 							if (error_row != nullptr)
 								error_row[bone] = error;
 							if (error > best_error)
@@ -691,6 +786,7 @@ namespace aclb200
 						}
 						else
 						{
+							const Qvv<V> object = load_planes(planes, plane_stride, bone);
 							float4* out = reinterpret_cast<float4*>(op.object_poses + pose * op.pose_stride + size_t(bone) * 48);
 							out[0] = make_float4(object.rotation.x, object.rotation.y, object.rotation.z, object.rotation.w);
 							out[1] = make_float4(object.translation.x, object.translation.y, object.translation.z, 0.0f);
@@ -792,9 +888,9 @@ namespace aclb200
 		}
 
 		// warps per block so that the object transform planes fit; 0 = the skeleton is too wide for shared memory
-		uint32_t warps_for(uint32_t plane_stride, uint32_t streams, int max_dynamic_smem)
+		uint32_t warps_for(uint32_t plane_stride, uint32_t floats_per_bone, int max_dynamic_smem)
 		{
-			const size_t per_warp = size_t(streams) * k_object_components * plane_stride * sizeof(float);
+			const size_t per_warp = size_t(floats_per_bone) * plane_stride * sizeof(float);
 			const size_t budget = max_dynamic_smem > 0 ? size_t(max_dynamic_smem) : 0;
 			if (per_warp > budget)
 				return 0;
@@ -825,6 +921,8 @@ namespace aclb200
 		cudaError_t error = cudaFuncSetAttribute(object_space_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin_limit);
 		if (error == cudaSuccess)
 			error = cudaFuncSetAttribute(object_space_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin_limit);
+		if (error == cudaSuccess)
+			error = cudaFuncSetAttribute(object_space_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin_limit);
 		return error;
 	}
 }
@@ -856,7 +954,7 @@ extern "C"
 		op.plane_stride = plane_stride_for(num_tracks);
 		op.flags = d_out_flags;
 		op.one = 1.0f;
-		const uint32_t warps = warps_for(op.plane_stride, 1, context->max_dynamic_smem);
+		const uint32_t warps = warps_for(op.plane_stride, k_object_components, context->max_dynamic_smem);
 		if (warps == 0)
 			return set_error(context, ACLB200_ERR_UNSUPPORTED, "local_to_object_space: the skeleton's object transforms do not fit in shared memory");
 
@@ -925,6 +1023,8 @@ extern "C"
 				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "calculate_compression_error: job has more tracks than a pose row holds");
 			if (d_output_indices == nullptr && job.num_tracks != clipset->host_clips[job.clip].num_tracks)
 				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "calculate_compression_error: raw and compressed track counts differ (pass output indices)");
+			if (job.error_metric > ACLB200_METRIC_QVVF_MATRIX3X4F || (job.error_metric != ACLB200_METRIC_QVVF && job.additive_format != 0))
+				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "calculate_compression_error: unknown error metric, or the matrix metric with an additive base (the reference does not implement that either)");
 			if (job.additive_format > 3 || (job.additive_format != 0 && (d_base_poses == nullptr || !is_transform)))
 				return set_error(context, ACLB200_ERR_INVALID_ARGUMENT, "calculate_compression_error: additive format out of range, or an additive job without base poses");
 			if (uint64_t(job.num_samples) * std::max(job.num_tracks, 1u) > 0xFFFFFFFFull)
@@ -933,14 +1033,15 @@ extern "C"
 			total_poses += job.num_samples;
 			widest = std::max(widest, job.num_tracks);
 		}
-		size_t group_begin[3] = { 0, 0, 0 };
-		for (uint32_t pass = 0; pass < 2; ++pass)
+		// groups: (rounding policy) x (error metric): each is decoded and measured by launches of its own
+		size_t group_begin[5] = { 0, 0, 0, 0, 0 };
+		for (uint32_t pass = 0; pass < 4; ++pass)
 		{
 			for (uint32_t index = 0; index < num_jobs; ++index)
 			{
 				const aclb200_error_job& job = jobs[index];
 				const bool stripped = (clipset->host_clips[job.clip].flags & k_clip_stripped) != 0;
-				if (stripped != (pass == 1))
+				if (stripped != ((pass >> 1) == 1) || (is_transform ? job.error_metric : 0u) != (pass & 1u))
 					continue;
 				ErrorJobDev dev = {};
 				dev.clip = job.clip;
@@ -960,21 +1061,27 @@ extern "C"
 		}
 
 		const uint32_t plane_stride = plane_stride_for(widest);
-		const uint32_t warps = is_transform ? warps_for(plane_stride, 2, context->max_dynamic_smem) : 8u;
-		if (warps == 0)
-			return set_error(context, ACLB200_ERR_UNSUPPORTED, "calculate_compression_error: the skeleton's object transforms do not fit in shared memory");
+		const uint32_t warps_by_metric[2] = { is_transform ? warps_for(plane_stride, 2 * k_object_components, context->max_dynamic_smem) : 8u,
+			is_transform ? warps_for(plane_stride, 2 * 12, context->max_dynamic_smem) : 8u };
+		for (uint32_t metric = 0; metric < 2; ++metric)
+		{
+			// groups are ordered (nearest, metric 0), (nearest, metric 1), (none, metric 0), (none, metric 1)
+			const size_t jobs_of_metric = (group_begin[metric + 1] - group_begin[metric]) + (group_begin[metric + 3] - group_begin[metric + 2]);
+			if (warps_by_metric[metric] == 0 && jobs_of_metric != 0)
+				return set_error(context, ACLB200_ERR_UNSUPPORTED, "calculate_compression_error: the skeleton's object transforms do not fit in shared memory");
+		}
 
 		// chunks: runs of jobs of one group whose decoded poses fit the scratch budget (one job at least)
 		const uint64_t budget_poses = std::max<uint64_t>(1, context->error_chunk_bytes / std::max<uint64_t>(stride, 1));
-		struct Chunk { size_t first_job, num_jobs; uint32_t num_poses; uint32_t rounding; };
+		struct Chunk { size_t first_job, num_jobs; uint32_t num_poses; uint32_t rounding; uint32_t metric; };
 		std::vector<Chunk> chunks;
 		uint64_t max_chunk_poses = 0;
-		for (uint32_t pass = 0; pass < 2; ++pass)
+		for (uint32_t pass = 0; pass < 4; ++pass)
 		{
 			size_t cursor = group_begin[pass];
 			while (cursor < group_begin[pass + 1])
 			{
-				Chunk chunk = { cursor, 0, 0, pass == 0 ? uint32_t(ACLB200_ROUND_NEAREST) : uint32_t(ACLB200_ROUND_NONE) };
+				Chunk chunk = { cursor, 0, 0, (pass >> 1) == 0 ? uint32_t(ACLB200_ROUND_NEAREST) : uint32_t(ACLB200_ROUND_NONE), pass & 1u };
 				uint64_t poses = 0;
 				while (cursor < group_begin[pass + 1] && (chunk.num_jobs == 0 || poses + ordered[cursor].num_samples <= budget_poses))
 				{
@@ -1063,10 +1170,14 @@ extern "C"
 
 			if (is_transform)
 			{
+				const uint32_t warps = warps_by_metric[chunk.metric];
 				const uint32_t blocks_needed = (chunk.num_poses + warps - 1) / warps;
 				const uint32_t blocks = std::min<uint32_t>(blocks_needed, uint32_t(context->num_sms) * 32);
-				const size_t smem = size_t(warps) * 2 * k_object_components * plane_stride * sizeof(float);
-				object_space_kernel<0><<<blocks, warps * 32, smem, cuda_stream>>>(p, ObjectSpaceParams{});
+				const size_t smem = size_t(warps) * 2 * (chunk.metric == 1 ? 12u : k_object_components) * plane_stride * sizeof(float);
+				if (chunk.metric == 1)
+					object_space_kernel<0, 1><<<blocks, warps * 32, smem, cuda_stream>>>(p, ObjectSpaceParams{});
+				else
+					object_space_kernel<0><<<blocks, warps * 32, smem, cuda_stream>>>(p, ObjectSpaceParams{});
 			}
 			else
 			{

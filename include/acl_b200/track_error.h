@@ -9,8 +9,9 @@
 // point directly (one launch sequence for the lot).
 //
 // Differences from the reference, all reported (never silent):
-//   * acl::qvvf_transform_error_metric and acl::additive_qvvf_transform_error_metric<format> (with the additive base overload) are
-//     implemented on the device; another metric (qvvf_matrix3x4f_transform_error_metric) throws acl_b200::error (ACLB200_ERR_UNSUPPORTED);
+//   * the reference's three metrics run on the device (qvvf_transform_error_metric, qvvf_matrix3x4f_transform_error_metric,
+//     additive_qvvf_transform_error_metric<format> with the additive base overload); a user defined metric throws acl_b200::error
+//     (ACLB200_ERR_UNSUPPORTED);
 //   * rtm::quat_normalize starts from the CPU's rsqrtss estimate in the reference: errors agree within 5e-5 on poses tens of units
 //     across (measured 1e-5), the worst track and its sample time are the reference's whenever its lead exceeds that.
 #pragma once
@@ -42,9 +43,14 @@ namespace acl_b200
 			return ~0u;
 		}
 
+		inline bool is_matrix_metric(const acl::itransform_error_metric& error_metric)
+		{
+			return std::strcmp(error_metric.get_name(), "qvvf_matrix3x4f_transform_error_metric") == 0;
+		}
+
 		template<class decompression_context_type>
 		inline acl::track_error measure_on_device(acl::iallocator& allocator, const acl::track_array& raw_tracks, decompression_context_type& context,
-			const acl::track_array_qvvf* additive_base_tracks = nullptr, uint32_t additive_format = 0)
+			const acl::track_array_qvvf* additive_base_tracks = nullptr, uint32_t additive_format = 0, uint32_t error_metric = ACLB200_METRIC_QVVF)
 		{
 			using settings_type = typename decompression_context_type::settings_type;
 			const acl::compressed_tracks& tracks = *context.get_compressed_tracks();
@@ -152,6 +158,7 @@ namespace acl_b200
 			job.duration = duration;
 			job.num_tracks = num_tracks;
 			job.additive_format = has_base ? additive_format : 0u;
+			job.error_metric = is_transform ? error_metric : 0u;
 			aclb200_track_error* d_out = static_cast<aclb200_track_error*>(d_result.get(device, sizeof(aclb200_track_error)));
 			device.check(aclb200_calculate_compression_error(device.get(), batch.clipset(), &job, 1, d_raw.get(device, 0),
 				is_transform ? static_cast<const uint32_t*>(d_parents.get(device, 0)) : nullptr, is_transform ? static_cast<const float*>(d_shells.get(device, 0)) : nullptr,
@@ -187,8 +194,10 @@ namespace acl_b200
 	{
 		ACL_ASSERT(raw_tracks.is_valid().empty(), "Raw tracks are invalid");
 		ACL_ASSERT(context.is_initialized(), "Context isn't initialized");
+		if (shim_impl::is_matrix_metric(error_metric))
+			return shim_impl::measure_on_device(allocator, raw_tracks, context, nullptr, 0, ACLB200_METRIC_QVVF_MATRIX3X4F);
 		if (raw_tracks.get_track_type() == acl::track_type8::qvvf && shim_impl::additive_format_of(error_metric) == ~0u)
-			throw error(ACLB200_ERR_UNSUPPORTED, std::string("calculate_compression_error: only the qvvf_transform_error_metric family runs on the device, not ") + error_metric.get_name());
+			throw error(ACLB200_ERR_UNSUPPORTED, std::string("calculate_compression_error: not one of the reference's error metrics: ") + error_metric.get_name());
 		return shim_impl::measure_on_device(allocator, raw_tracks, context);
 	}
 

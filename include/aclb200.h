@@ -245,6 +245,15 @@ typedef struct aclb200_track_error
 	uint32_t flags;					/* ACLB200_ERROR_FLAG_* */
 } aclb200_track_error;
 
+/* acl::itransform_error_metric implementations (compression/transform_error_metrics.h) */
+enum
+{
+	ACLB200_METRIC_QVVF = 0,				/* qvvf_transform_error_metric (:281-385), and additive_qvvf_transform_error_metric<format> (:470-526) for the
+											 * jobs that carry an additive_format */
+	ACLB200_METRIC_QVVF_MATRIX3X4F = 1		/* qvvf_matrix3x4f_transform_error_metric (:389-464): transforms as 3x4 matrices (for rigs with shear);
+											 * every operation is IEEE exact: bit-identical to the reference on any CPU */
+};
+
 enum
 {
 	ACLB200_ERROR_FLAG_NEGATIVE_SCALE = 1,		/* informational: a negative scale took rtm::qvv_mul through its matrix branch (qvvf.h:320-345) somewhere */
@@ -266,7 +275,7 @@ typedef struct aclb200_error_job
 	uint32_t skeleton_offset;		/* first entry of this clip's skeleton in d_parent_indices / d_shell_distances / d_output_indices */
 	uint64_t first_raw_pose;		/* pose index of sample 0 in d_raw_poses */
 	uint32_t additive_format;		/* acl::additive_clip_format8 (core/additive_utils.h:42-66): 0 none, 1 relative, 2 additive0, 3 additive1 */
-	uint32_t reserved;				/* 0 */
+	uint32_t error_metric;			/* ACLB200_METRIC_* (transform clip sets) */
 	uint64_t first_base_pose;		/* additive jobs: pose index of sample 0 in d_base_poses */
 } aclb200_error_job;
 

@@ -1464,14 +1464,11 @@ static void rtm_quat_from_matrix(float m[3][3], int normalize_mode, float out[4]
 	memcpy(out, q, sizeof(q));
 }
 
-/* The negative scale branch of rtm::qvv_mul, qvvf.h:320-345: through matrices (matrix_mul matrix3x4f.h:298-321 with
- * vector_mul_add = (v0 * v1) + v2 on SSE2, matrix_remove_scale :636-644 = vector_normalize3(axis, axis, 1e-8) vector4f.h:2310-2318,
- * the result's sign bits xor-ed onto the axes) */
-static void qvv_mul_negative_scale(const float lhs[12], const float rhs[12], int normalize_mode, float out[12])
+/* rtm::matrix_mul(lhs, rhs), matrix3x4f.h:298-321: per row tmp = l.x * r.x_axis; tmp = l.y * r.y_axis + tmp; tmp = l.z * r.z_axis + tmp
+ * (vector_mul_add = (v0 * v1) + v2 on SSE2); the translation row adds r.w_axis */
+static void rtm_matrix_mul(float l[4][3], float r[4][3], float out[4][3])
 {
-	float l[4][3], r[4][3], m[4][3];
-	rtm_matrix_from_qvv(lhs, l);
-	rtm_matrix_from_qvv(rhs, r);
+	float m[4][3];
 	for (int row = 0; row < 4; ++row)
 		for (int c = 0; c < 3; ++c)
 		{
@@ -1480,6 +1477,18 @@ static void qvv_mul_negative_scale(const float lhs[12], const float rhs[12], int
 			tmp = l[row][2] * r[2][c] + tmp;
 			m[row][c] = row == 3 ? r[3][c] + tmp : tmp;
 		}
+	memcpy(out, m, sizeof(m));
+}
+
+/* The negative scale branch of rtm::qvv_mul, qvvf.h:320-345: through matrices (matrix_mul matrix3x4f.h:298-321 with
+ * vector_mul_add = (v0 * v1) + v2 on SSE2, matrix_remove_scale :636-644 = vector_normalize3(axis, axis, 1e-8) vector4f.h:2310-2318,
+ * the result's sign bits xor-ed onto the axes) */
+static void qvv_mul_negative_scale(const float lhs[12], const float rhs[12], int normalize_mode, float out[12])
+{
+	float l[4][3], r[4][3], m[4][3];
+	rtm_matrix_from_qvv(lhs, l);
+	rtm_matrix_from_qvv(rhs, r);
+	rtm_matrix_mul(l, r, m);
 	float scale[3];
 	for (int i = 0; i < 3; ++i)
 		scale[i] = lhs[8 + i] * rhs[8 + i];
@@ -1650,6 +1659,52 @@ float aclo_calculate_error(const float* raw_object_bone, const float* lossy_obje
 	return sse_max_ss(sse_max_ss(errors[0], errors[1]), errors[2]);
 }
 
+/* qvvf_matrix3x4f_transform_error_metric (transform_error_metrics.h:389-464): convert_transforms = matrix_from_qvv per bone,
+ * local_to_object_space = matrix_mul(local, parent object) (roots copied), into out_object [num_tracks][4][3] */
+static int matrix_local_to_object_space(const float* local_pose, const uint32_t* parent_indices, uint32_t num_tracks, float* out_object)
+{
+	for (uint32_t bone = 0; bone < num_tracks; ++bone)
+	{
+		float local[4][3];
+		rtm_matrix_from_qvv(local_pose + (size_t)bone * 12, local);
+		float (*object)[3] = (float (*)[3])(out_object + (size_t)bone * 12);
+		const uint32_t parent = parent_indices[bone];
+		if (parent == 0xFFFFFFFFu)
+			memcpy(object, local, sizeof(local));
+		else if (parent >= bone)
+			return -1;
+		else
+			rtm_matrix_mul(local, (float (*)[3])(out_object + (size_t)parent * 12), object);
+	}
+	return 0;
+}
+
+/* calculate_error of the matrix metric (:438-463): rtm::matrix_mul_point3 (matrix3x4f.h:326-336: tmp0 = p.x * x_axis; tmp0 = p.y * y_axis + tmp0;
+ * tmp1 = p.z * z_axis + w_axis; tmp0 + tmp1) of the three shell points, distances, the largest */
+static float matrix_calculate_error(const float* raw_object, const float* lossy_object, float shell_distance)
+{
+	float errors[3];
+	for (int axis = 0; axis < 3; ++axis)
+	{
+		float point[3] = { 0.0f, 0.0f, 0.0f };
+		point[axis] = shell_distance;
+		float vtx[2][3];
+		for (int stream = 0; stream < 2; ++stream)
+		{
+			const float (*m)[3] = (const float (*)[3])(stream == 0 ? raw_object : lossy_object);
+			for (int c = 0; c < 3; ++c)
+			{
+				float tmp0 = point[0] * m[0][c];
+				tmp0 = point[1] * m[1][c] + tmp0;
+				const float tmp1 = point[2] * m[2][c] + m[3][c];
+				vtx[stream][c] = tmp0 + tmp1;
+			}
+		}
+		errors[axis] = vector_distance3(vtx[0], vtx[1]);
+	}
+	return sse_max_ss(sse_max_ss(errors[0], errors[1]), errors[2]);
+}
+
 /* The sample loop of calculate_transform_track_error (track_error.impl.h:225-392) once both pose streams are sampled:
  * raw_poses = raw_tracks.sample_tracks(t_i), lossy_poses = seek(t_i) + decompress_tracks (already remapped, :341), both
  * [num_samples][num_tracks][12]; t_i = min(i / sample_rate, duration) (:337). base_poses (optional): the additive base sampled at the matching
@@ -1658,7 +1713,7 @@ float aclo_calculate_error(const float* raw_object_bone, const float* lossy_obje
 int aclo_transform_track_error(const float* raw_poses, const float* lossy_poses, uint32_t num_samples, uint32_t num_tracks,
 	float sample_rate, float duration, const uint32_t* parent_indices, const float* shell_distances, int normalize_mode,
 	aclo_track_error* out_error, float* out_errors, float* scratch_object_poses /* [4][num_tracks][12] */,
-	const float* base_poses /* [num_samples][num_tracks][12] or NULL */, uint32_t additive_format)
+	const float* base_poses /* [num_samples][num_tracks][12] or NULL */, uint32_t additive_format, uint32_t metric /* 0 qvvf, 1 qvvf_matrix3x4f */)
 {
 	out_error->index = 0xFFFFFFFFu;		/* track_error(), track_error.h:48-62 */
 	out_error->error = 0.0f;
@@ -1689,14 +1744,17 @@ int aclo_transform_track_error(const float* raw_poses, const float* lossy_poses,
 			raw_local = raw_applied;
 			lossy_local = lossy_applied;
 		}
-		const int r0 = aclo_local_to_object_space(raw_local, parent_indices, num_tracks, normalize_mode, raw_object);
-		const int r1 = aclo_local_to_object_space(lossy_local, parent_indices, num_tracks, normalize_mode, lossy_object);
+		const int r0 = metric == 1 ? matrix_local_to_object_space(raw_local, parent_indices, num_tracks, raw_object)
+			: aclo_local_to_object_space(raw_local, parent_indices, num_tracks, normalize_mode, raw_object);
+		const int r1 = metric == 1 ? matrix_local_to_object_space(lossy_local, parent_indices, num_tracks, lossy_object)
+			: aclo_local_to_object_space(lossy_local, parent_indices, num_tracks, normalize_mode, lossy_object);
 		if (r0 < 0 || r1 < 0)
 			return -1;
 		negative |= r0 | r1;
 		for (uint32_t bone = 0; bone < num_tracks; ++bone)
 		{
-			const float error = aclo_calculate_error(raw_object + (size_t)bone * 12, lossy_object + (size_t)bone * 12, shell_distances[bone]);
+			const float error = metric == 1 ? matrix_calculate_error(raw_object + (size_t)bone * 12, lossy_object + (size_t)bone * 12, shell_distances[bone])
+				: aclo_calculate_error(raw_object + (size_t)bone * 12, lossy_object + (size_t)bone * 12, shell_distances[bone]);
 			if (out_errors != NULL)
 				out_errors[(size_t)sample * num_tracks + bone] = error;
 			if (error > out_error->error)		/* :367-372 */

@@ -138,7 +138,8 @@ float aclo_calculate_error(const float* raw_object_bone, const float* lossy_obje
 int aclo_transform_track_error(const float* raw_poses, const float* lossy_poses, uint32_t num_samples, uint32_t num_tracks,
 	float sample_rate, float duration, const uint32_t* parent_indices, const float* shell_distances, int normalize_mode,
 	aclo_track_error* out_error, float* out_errors, float* scratch_object_poses /* [4][num_tracks][12] */,
-	const float* base_poses /* optional additive base, [num_samples][num_tracks][12] */, uint32_t additive_format);
+	const float* base_poses /* optional additive base, [num_samples][num_tracks][12] */, uint32_t additive_format,
+	uint32_t metric /* 0 qvvf_transform_error_metric, 1 qvvf_matrix3x4f_transform_error_metric (transform_error_metrics.h:389-464; no CPU specific step) */);
 /* acl::apply_additive_to_base (core/additive_utils.h:131-167) over a pose, in place on `pose`; format = acl::additive_clip_format8 */
 int aclo_apply_additive_to_base(uint32_t additive_format, const float* base_pose, float* pose, uint32_t num_tracks, int normalize_mode);
 int aclo_scalar_track_error(const float* raw_values, const float* lossy_values, uint32_t num_samples, uint32_t num_tracks, uint32_t components,

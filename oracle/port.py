@@ -253,7 +253,7 @@ def local_to_object_space(local_pose: np.ndarray, parents: np.ndarray, normalize
 
 def transform_track_error(raw_poses: np.ndarray, lossy_poses: np.ndarray, sample_rate: float, duration: float, parents: np.ndarray,
                           shell_distances: np.ndarray, normalize_mode: int = NORMALIZE_IEEE, base_poses: np.ndarray | None = None,
-                          additive_format: int = 0):
+                          additive_format: int = 0, metric: int = 0):
     """The loop of calculate_transform_track_error over [num_samples][num_tracks][12] poses.
     Returns (TrackError, errors float32 [num_samples][num_tracks], negative_scale_seen)."""
     raw_poses = np.ascontiguousarray(raw_poses, dtype=np.float32)
@@ -270,10 +270,10 @@ def transform_track_error(raw_poses: np.ndarray, lossy_poses: np.ndarray, sample
     result = TrackError()
     fn = lib().aclo_transform_track_error
     fn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
-                   C.POINTER(TrackError), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+                   C.POINTER(TrackError), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     rc = fn(raw_poses.ctypes.data, lossy_poses.ctypes.data, num_samples, num_tracks, sample_rate, duration, parents.ctypes.data,
             shell_distances.ctypes.data, normalize_mode, C.byref(result), errors.ctypes.data, scratch.ctypes.data,
-            None if base_poses is None else base_poses.ctypes.data, additive_format)
+            None if base_poses is None else base_poses.ctypes.data, additive_format, metric)
     if rc < 0:
         raise RuntimeError("aclo_transform_track_error: a parent does not precede its child")
     return result, errors, rc == 1

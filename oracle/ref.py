@@ -412,3 +412,20 @@ def transform_error_additive(spec: TransformSpec, blob: np.ndarray, base_spec: T
     out.update(index=int(result.index), error=float(result.error), sample_time=float(result.sample_time), rounding=int(rounding.value),
                sample_rate=float(spec.sample_rate), duration=finite_duration(m, spec.sample_rate), additive_format=additive_format)
     return out
+
+
+METRIC_QVVF, METRIC_QVVF_MATRIX3X4F = 0, 1
+
+
+def transform_error_matrix(spec: TransformSpec, blob: np.ndarray) -> dict:
+    """calculate_compression_error with qvvf_matrix3x4f_transform_error_metric (debug settings): index / error / sample_time and the per bone
+    errors float32 [num_samples][num_tracks] replayed with the metric's own functions. The poses are transform_error(spec, blob, 1)'s."""
+    errors = np.zeros((spec.num_samples, spec.num_tracks), np.float32)
+    result = TrackError()
+    fn = lib().aclref_transform_error_matrix
+    fn.argtypes = [C.POINTER(_TransformSpec), C.c_void_p, C.POINTER(TrackError), C.c_void_p]
+    c_spec = spec.to_c()
+    rc = fn(C.byref(c_spec), blob.ctypes.data, C.byref(result), errors.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"aclref_transform_error_matrix failed ({rc})")
+    return dict(index=int(result.index), error=float(result.error), sample_time=float(result.sample_time), errors=errors)

@@ -1123,6 +1123,82 @@ extern "C"
 		return 0;
 	}
 
+	// calculate_compression_error with the reference's other metric, qvvf_matrix3x4f_transform_error_metric (transform_error_metrics.h:389-464:
+	// transforms converted to 3x4 matrices, object space by matrix_mul, shell points through matrix_mul_point3). Same raw / decoded poses as
+	// aclref_transform_error (debug settings); out_errors [num_samples][num_tracks] replayed with the metric's own functions.
+	int aclref_transform_error_matrix(const aclref_transform_spec* spec, const void* blob, aclref_track_error* out_error, float* out_errors)
+	{
+		const compressed_tracks& tracks = *static_cast<const compressed_tracks*>(blob);
+		if (tracks.get_track_type() != track_type8::qvvf || tracks.get_num_tracks() != spec->num_tracks)
+			return -2;
+		iallocator& alloc = allocator();
+		track_array_qvvf raw_tracks(alloc, spec->num_tracks);
+		make_transform_tracks(*spec, raw_tracks);
+		decompression_context<settings_debug> context;
+		if (!context.initialize(tracks))
+			return -1;
+
+		const qvvf_matrix3x4f_transform_error_metric error_metric;
+		const track_error result = calculate_compression_error(alloc, raw_tracks, context, error_metric);
+		out_error->index = result.index;
+		out_error->error = result.error;
+		out_error->sample_time = result.sample_time;
+		if (out_errors == nullptr)
+			return 0;
+
+		const sample_rounding_policy rounding = (tracks.has_database() || tracks.has_stripped_keyframes()) ? sample_rounding_policy::none : sample_rounding_policy::nearest;
+		const uint32_t num_tracks = raw_tracks.get_num_tracks();
+		const uint32_t num_samples = raw_tracks.get_num_samples_per_track();
+		std::vector<uint32_t> parents(num_tracks), self(num_tracks);
+		for (uint32_t bone = 0; bone < num_tracks; ++bone)
+		{
+			parents[bone] = raw_tracks[bone].get_description().parent_index;
+			self[bone] = bone;
+		}
+		acl_impl::debug_track_writer raw_writer(alloc, track_type8::qvvf, num_tracks);
+		acl_impl::debug_track_writer lossy_writer(alloc, track_type8::qvvf, num_tracks);
+		lossy_writer.initialize_with_defaults(raw_tracks);
+		std::vector<rtm::matrix3x4f> raw_local(num_tracks), lossy_local(num_tracks), raw_object(num_tracks), lossy_object(num_tracks);
+
+		itransform_error_metric::convert_transforms_args convert_args;
+		convert_args.dirty_transform_indices = self.data();
+		convert_args.num_dirty_transforms = num_tracks;
+		convert_args.num_transforms = num_tracks;
+		convert_args.is_additive_base = false;
+		itransform_error_metric::local_to_object_space_args object_args;
+		object_args.dirty_transform_indices = self.data();
+		object_args.num_dirty_transforms = num_tracks;
+		object_args.parent_transform_indices = parents.data();
+		object_args.num_transforms = num_tracks;
+		for (uint32_t sample = 0; sample < num_samples; ++sample)
+		{
+			const float sample_time = rtm::scalar_min(float(sample) / raw_tracks.get_sample_rate(), raw_tracks.get_finite_duration());
+			raw_tracks.sample_tracks(sample_time, rounding, raw_writer);
+			context.seek(sample_time, rounding);
+			context.decompress_tracks(lossy_writer);
+			convert_args.sample_index = sample;
+			convert_args.transforms = raw_writer.tracks_typed.qvvf;
+			convert_args.is_lossy = false;
+			error_metric.convert_transforms(convert_args, raw_local.data());
+			convert_args.transforms = lossy_writer.tracks_typed.qvvf;
+			convert_args.is_lossy = true;
+			error_metric.convert_transforms(convert_args, lossy_local.data());
+			object_args.local_transforms = raw_local.data();
+			error_metric.local_to_object_space(object_args, raw_object.data());
+			object_args.local_transforms = lossy_local.data();
+			error_metric.local_to_object_space(object_args, lossy_object.data());
+			for (uint32_t bone = 0; bone < num_tracks; ++bone)
+			{
+				itransform_error_metric::calculate_error_args error_args;
+				error_args.transform0 = &raw_object[bone];
+				error_args.transform1 = &lossy_object[bone];
+				error_args.construct_sphere_shell(raw_tracks[bone].get_description().shell_distance);
+				out_errors[size_t(sample) * num_tracks + bone] = rtm::scalar_cast(error_metric.calculate_error(error_args));
+			}
+		}
+		return 0;
+	}
+
 	// The scalar flavour: calculate_compression_error(allocator, raw_tracks, context) (track_error.impl.h:400-463 -> calculate_scalar_track_error
 	// :166-223). out_raw_values [num_samples][num_tracks][4] = raw_tracks.sample_tracks(...) (first N components of each row).
 	int aclref_scalar_error(const aclref_scalar_spec* spec, const void* blob, aclref_track_error* out_error, uint32_t* out_rounding, float* out_raw_values)

@@ -151,6 +151,21 @@ int main()
 			const acl::track_error reference = measure<acl::decompression_context<acl::debug_transform_decompression_settings>>(*compressed, raw, false);
 			const acl::track_error ours = reference_only ? reference : measure<acl_b200::decompression_context<acl::debug_transform_decompression_settings>>(*compressed, raw, true);
 			ok = check(c.name, reference, ours, 5.0e-5F) && ok;
+
+			// the matrix metric has no CPU specific step: exact
+			{
+				acl::decompression_context<acl::debug_transform_decompression_settings> reference_context;
+				acl_b200::decompression_context<acl::debug_transform_decompression_settings> our_context;
+				if (!reference_context.initialize(*compressed) || (!reference_only && !our_context.initialize(*compressed)))
+					return 1;
+				const acl::qvvf_matrix3x4f_transform_error_metric matrix_metric;
+				const acl::track_error matrix_reference = acl::calculate_compression_error(g_allocator, raw, reference_context, matrix_metric);
+				const acl::track_error matrix_ours = reference_only ? matrix_reference : acl_b200::calculate_compression_error(g_allocator, raw, our_context, matrix_metric);
+				const bool exact = matrix_reference.index == matrix_ours.index && matrix_reference.error == matrix_ours.error && matrix_reference.sample_time == matrix_ours.sample_time;
+				std::printf("%s, qvvf_matrix3x4f metric: reference (track %u, error %.9g) ours (track %u, error %.9g) %s\n", c.name, matrix_reference.index,
+					double(matrix_reference.error), matrix_ours.index, double(matrix_ours.error), exact ? "ok" : "MISMATCH");
+				ok = exact && ok;
+			}
 			g_allocator.deallocate(compressed, compressed->get_size());
 		}
 

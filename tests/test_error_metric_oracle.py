@@ -115,6 +115,21 @@ def test_port_matches_live_reference_additive(reference, oracle_port, name, addi
     assert abs(ieee.error - r["error"]) <= tolerance
 
 
+@pytest.mark.parametrize("name", list(clips.TRANSFORM_SPECS) + ["mirrored"])
+def test_port_matrix_metric_matches_live_reference_bit_for_bit(reference, oracle_port, name):
+    """qvvf_matrix3x4f_transform_error_metric (transform_error_metrics.h:389-464): matrix_from_qvv, matrix_mul down the hierarchy,
+    matrix_mul_point3 of the shell points. No CPU specific step: one flavour, bit for bit."""
+    spec = mirrored_spec("mixed_scale", 30) if name == "mirrored" else clips.TRANSFORM_SPECS[name]
+    blob = reference.compress_transform(spec) if name == "mirrored" else clips.load_blob(name)
+    r = reference.transform_error(spec, blob, 1)
+    m = reference.transform_error_matrix(spec, blob)
+    for mode in (P.NORMALIZE_RTM_SSE2, P.NORMALIZE_IEEE):       # the normalisation flavour must not matter to this metric
+        got, errors, _ = oracle_port.transform_track_error(r["raw_poses"], r["lossy_poses"], r["sample_rate"], r["duration"], r["parents"],
+                                                           r["shell_distances"], mode, metric=1)
+        assert clips.bit_equal(errors, m["errors"]), name
+        assert (got.index, np.float32(got.error), np.float32(got.sample_time)) == (m["index"], np.float32(m["error"]), np.float32(m["sample_time"])), name
+
+
 MIRRORED_CASES = [("mixed_scale", 30), ("c1_30bones", 20), ("ragged_17", 50), ("single_segment", 100)]
 
 

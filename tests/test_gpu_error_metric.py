@@ -237,6 +237,37 @@ def test_compression_error_with_negative_scales(gpu, name, negative_scale_pct):
     clipset.release()
 
 
+@pytest.mark.parametrize("name", ["c1_30bones", "c2_100bones", "mixed_scale", "stripped_single", "paragon_like", "ragged_17", "one_bone", "mirrored"])
+def test_matrix_metric_matches_the_reference_exactly(gpu, name):
+    """ACLB200_METRIC_QVVF_MATRIX3X4F == qvvf_matrix3x4f_transform_error_metric: no CPU specific step, so the device must give the
+    reference's numbers bit for bit (every per bone error, the worst track, its error and sample time); measured next to a job of the
+    same clip with the default metric in one call."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("needs oracle/_ref/libaclref.so")
+    ab = gpu["ab"]
+    spec = mirrored_spec("mixed_scale", 30) if name == "mirrored" else clips.TRANSFORM_SPECS[name]
+    blob = ref.compress_transform(spec) if name == "mirrored" else clips.load_blob(name)
+    clipset = gpu["ctx"].upload([blob])
+    r = ref.transform_error(spec, blob, 1)
+    m = ref.transform_error_matrix(spec, blob)
+    common = dict(clip=0, num_samples=spec.num_samples, sample_rate=r["sample_rate"], duration=r["duration"], num_tracks=spec.num_tracks)
+    jobs = _jobs(gpu, [dict(common), dict(common, error_metric=ab.api.METRIC_QVVF_MATRIX3X4F)])
+    got, matrix = _measure(gpu, clipset, jobs, r["raw_poses"], r["parents"], r["shell_distances"], _options(gpu, 1))
+    rows = matrix[spec.num_samples:2 * spec.num_samples, :spec.num_tracks]
+    assert clips.bit_equal(rows, m["errors"]), name
+    assert (int(got[1]["index"]), np.float32(got[1]["error"]), np.float32(got[1]["sample_time"]), int(got[1]["flags"])) == \
+        (m["index"], np.float32(m["error"]), np.float32(m["sample_time"]), 0), name
+    want, want_errors, _ = gpu["port"].transform_track_error(r["raw_poses"], r["lossy_poses"], r["sample_rate"], r["duration"], r["parents"],
+                                                             r["shell_distances"], gpu["port"].NORMALIZE_IEEE)
+    assert clips.bit_equal(matrix[:spec.num_samples, :spec.num_tracks], want_errors), (name, "default metric job next to it")
+    # the reference does not implement an additive base for this metric: refused, not guessed
+    with pytest.raises(ab.AclB200Error):
+        _measure(gpu, clipset, _jobs(gpu, [dict(common, error_metric=1, additive_format=2)]), r["raw_poses"], r["parents"], r["shell_distances"], _options(gpu, 1),
+                 base_poses=r["raw_poses"])
+    clipset.release()
+
+
 def test_output_indices_remap(gpu):
     """remap_output (track_error.impl.h:522-532): a raw track the compressed clip does not output is measured with its raw value."""
     port = gpu["port"]
