@@ -214,4 +214,66 @@ namespace acl_b200
 			throw error(ACLB200_ERR_UNSUPPORTED, std::string("calculate_compression_error: only the qvvf_transform_error_metric family runs on the device, not ") + error_metric.get_name());
 		return shim_impl::measure_on_device(allocator, raw_tracks, context, &additive_base_tracks, additive_format);
 	}
+
+	// calculate_compression_error(allocator, context0, context1), compression/track_error.h:109-121 (impl/track_error.impl.h:690-750): the worst
+	// difference between two compressed clips, scalar tracks only. Composition of two device calls: every sample of context0's clip is decoded
+	// into device memory (aclb200_decompress_all_samples) and plays the raw side of the measurement of context1's clip. Both contexts must
+	// live on the same device.
+	template<class settings_type0, class settings_type1>
+	inline acl::track_error calculate_compression_error(acl::iallocator& allocator, decompression_context<settings_type0>& context0, decompression_context<settings_type1>& context1)
+	{
+		(void)allocator;
+		ACL_ASSERT(context0.is_initialized(), "Context isn't initialized");
+		ACL_ASSERT(context1.is_initialized(), "Context isn't initialized");
+		const acl::compressed_tracks* tracks0 = context0.get_compressed_tracks();
+		const acl::compressed_tracks* tracks1 = context1.get_compressed_tracks();
+		if (tracks0->get_track_type() == acl::track_type8::qvvf)
+			return acl::acl_impl::invalid_track_error();	// Only supports scalar tracks
+		const uint32_t num_samples = tracks0->get_num_samples_per_track();
+		const uint32_t num_tracks = tracks0->get_num_tracks();
+		if (num_samples == 0 || num_tracks == 0)
+			return acl::track_error();
+
+		batch_decompressor& batch0 = context0.device_batch();
+		batch_decompressor& batch1 = context1.device_batch();
+		device_context& device = batch1.device();
+		if (&batch0.device() != &device)
+			throw error(ACLB200_ERR_INVALID_ARGUMENT, "calculate_compression_error(context0, context1): the contexts live on different devices");
+		if (batch0.info().track_type != batch1.info().track_type || tracks1->get_num_tracks() != num_tracks)
+			throw error(ACLB200_ERR_INVALID_ARGUMENT, "calculate_compression_error(context0, context1): the clips do not hold the same tracks");
+
+		aclb200_options options;
+		std::memset(&options, 0, sizeof(options));
+		aclb200_default_options(&options);
+		// nearest, unless either clip misses key frames (track_error.impl.h:741-745)
+		const bool interpolate = tracks0->has_database() || tracks1->has_database() || tracks0->has_stripped_keyframes() || tracks1->has_stripped_keyframes();
+		options.rounding_policy = interpolate ? ACLB200_ROUND_NONE : ACLB200_ROUND_NEAREST;
+
+		aclb200_error_job job;
+		std::memset(&job, 0, sizeof(job));
+		job.clip = 0;
+		job.num_samples = num_samples;
+		job.sample_rate = tracks0->get_sample_rate();
+		job.duration = tracks0->get_finite_duration();
+		job.num_tracks = num_tracks;
+
+		const uint32_t components = batch0.info().track_type <= 3 ? batch0.info().track_type + 1 : 4u;
+		shim_impl::device_buffer d_first, d_result;
+		void* d_samples = d_first.get(device, size_t(num_samples) * num_tracks * components * sizeof(float));
+		options.looping_policy = static_cast<uint32_t>(context0.get_looping_policy());
+		device.check(aclb200_decompress_all_samples(device.get(), batch0.clipset(), &job, 1, &options, d_samples, nullptr), "aclb200_decompress_all_samples");
+		aclb200_track_error* d_out = static_cast<aclb200_track_error*>(d_result.get(device, sizeof(aclb200_track_error)));
+		options.rounding_policy = ACLB200_ROUND_NONE;		// the measurement picks the policy itself, from the clip it decodes (scalar clips never
+																	// strip key frames, so both sides are sought with `nearest` like the reference's)
+		options.looping_policy = static_cast<uint32_t>(context1.get_looping_policy());
+		device.check(aclb200_calculate_compression_error(device.get(), batch1.clipset(), &job, 1, d_samples, nullptr, nullptr, nullptr, nullptr, &options, d_out, nullptr, nullptr),
+			"aclb200_calculate_compression_error");
+		aclb200_track_error result;
+		device.check(aclb200_copy_to_host(device.get(), &result, d_out, sizeof(result)), "result download");
+		acl::track_error out;
+		out.index = result.index;
+		out.error = result.error;
+		out.sample_time = result.sample_time;
+		return out;
+	}
 }

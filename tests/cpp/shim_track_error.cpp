@@ -68,14 +68,14 @@ namespace
 		return tracks;
 	}
 
-	acl::track_array_float3f make_scalar_clip(uint32_t num_tracks, uint32_t num_samples)
+	acl::track_array_float3f make_scalar_clip(uint32_t num_tracks, uint32_t num_samples, float precision = 0.001F)
 	{
 		acl::track_array_float3f tracks(g_allocator, num_tracks);
 		for (uint32_t index = 0; index < num_tracks; ++index)
 		{
 			acl::track_desc_scalarf desc;
 			desc.output_index = index;
-			desc.precision = 0.001F;
+			desc.precision = precision;
 			acl::track_float3f track = acl::track_float3f::make_reserve(desc, g_allocator, num_samples, 30.0F);
 			for (uint32_t sample = 0; sample < num_samples; ++sample)
 			{
@@ -210,6 +210,20 @@ int main()
 			const acl::track_error reference = acl::calculate_compression_error(g_allocator, raw, reference_context);
 			const acl::track_error ours = reference_only ? reference : acl_b200::calculate_compression_error(g_allocator, raw, our_context);
 			ok = check("scalar float3f 19 x 45", reference, ours, 0.0F) && ok;
+
+			// calculate_compression_error(allocator, context0, context1) (track_error.h:109-121): the same raw clip compressed coarsely
+			const acl::track_array_float3f coarse_raw = make_scalar_clip(19, 45, 0.05F);
+			acl::compressed_tracks* coarse = nullptr;
+			if (acl::compress_track_list(g_allocator, coarse_raw, acl::compression_settings(), coarse, stats).any())
+				return 1;
+			acl::decompression_context<acl::default_scalar_decompression_settings> reference_coarse;
+			acl_b200::decompression_context<acl::default_scalar_decompression_settings> our_coarse;
+			if (!reference_coarse.initialize(*coarse) || (!reference_only && !our_coarse.initialize(*coarse)))
+				return 1;
+			const acl::track_error pair_reference = acl::calculate_compression_error(g_allocator, reference_context, reference_coarse);
+			const acl::track_error pair_ours = reference_only ? pair_reference : acl_b200::calculate_compression_error(g_allocator, our_context, our_coarse);
+			ok = check("scalar float3f, fine clip against coarse clip", pair_reference, pair_ours, 0.0F) && ok;
+			g_allocator.deallocate(coarse, coarse->get_size());
 			g_allocator.deallocate(compressed, compressed->get_size());
 		}
 	}
