@@ -1,5 +1,5 @@
 """Profiling driver for the 8(f1) path: aclb200_calculate_compression_error over N reference-compressed C2-like clips, a few calls.
-Used under ncu (see tools/profile_error_metric.sh); prints the per clip agreement with the reference on a small sample."""
+Used under ncu (`ncu --set full -k regex:object_space_kernel -c 1 python tools/profile_error_metric.py 1024 1`); prints the per clip agreement with the reference on a small sample."""
 import os
 import sys
 import time
