@@ -111,7 +111,7 @@ extern "C"
 {
 	const char* aclb200_version_string(void)
 	{
-		return "aclb200 0.1 (sm_100a; ACL compressed_tracks v02_00_00..v02_01_00)";
+		return "aclb200 0.3 (sm_100a; ACL compressed_tracks v02_00_00..v02_01_00)";
 	}
 
 	const char* aclb200_status_string(aclb200_status status)

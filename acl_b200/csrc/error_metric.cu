@@ -1,10 +1,13 @@
 // acl_b200/csrc/error_metric.cu -- SURVEY 8(f1) + 8(f3): the nearest caller of the decode hot path inside ACL, on the device.
 //
-//   * aclb200_calculate_compression_error: acl::calculate_compression_error (includes/acl/compression/impl/track_error.impl.h:400-571
+//   * aclb200_calculate_compression_error: acl::calculate_compression_error (includes/acl/compression/impl/track_error.impl.h:400-680
 //     -> calculate_transform_track_error :225-392 / calculate_scalar_track_error :166-223) for MANY clips per call: every sample of every
-//     clip is decoded by the decompress_tracks pipeline (pipeline.cu), taken to object space and measured against the raw pose with the
-//     qvvf_transform_error_metric (includes/acl/compression/transform_error_metrics.h:281-385); one {index, error, sample_time} per clip
-//     comes back, the poses never leave the GPU.
+//     clip is decoded by the decompress_tracks pipeline (pipeline.cu), taken to object space and measured against the raw pose with one of
+//     the reference's metrics (includes/acl/compression/transform_error_metrics.h: qvvf_transform_error_metric :281-385,
+//     qvvf_matrix3x4f_transform_error_metric :389-464, additive_qvvf_transform_error_metric<format> :470-526 with its additive base);
+//     one {index, error, sample_time} per clip comes back, the poses never leave the GPU.
+//   * aclb200_decompress_all_samples: the sampling loop of that measurement and of acl::convert_track_list (impl/convert.impl.h:146-232)
+//     as an entry point of its own.
 //   * aclb200_local_to_object_space: qvvf_transform_error_metric::local_to_object_space (transform_error_metrics.h:289-310) as a pose
 //     consumer of its own (the hierarchy walk a skinning / blending stage starts with).
 //
@@ -12,11 +15,15 @@
 // the warp takes 32 consecutive bones at a time and resolves them in wavefronts: a lane whose parent lies in an earlier chunk -- or was
 // finished by an earlier wavefront of this chunk -- computes, the others wait for the next wavefront (skeletons are shallow and bushy:
 // a handful of wavefronts per chunk). Object transforms live in shared memory as [component][bone] planes so that 32 lanes reading 32
-// different parents hit 32 different banks. The measurement itself (three shell points through both transforms) runs after the chunk's
-// wavefronts with every lane busy, and the raw and the lossy pose travel together as packed f32x2 values. Every float operation is the reference's, in its order, never fused (the library is built
-// with --fmad=false); the one exception is rtm::quat_normalize, whose SSE2 code starts from the CPU specific rsqrtss estimate
-// (external/rtm/includes/rtm/quatf.h:917-953) and cannot be reproduced bit for bit by anyone: the IEEE 1 / sqrt stands in for it
-// (the tests' CPU restatement has both; errors agree with the reference within 5e-5 on poses tens of units across, tests/test_gpu_error_metric.py).
+// different parents hit 32 different banks; a bone's local transform is parked in the slot its object transform will take. The
+// measurement itself (three shell points through both transforms) runs after the chunk's wavefronts with every lane busy, and the raw and
+// the lossy pose travel together as packed f32x2 values (FMUL2 / FFMA2).
+//
+// Every float operation is the reference's, in its order, never fused (the library is built with --fmad=false, packed adds go through a
+// run-time 1.0f). The one exception is rtm::quat_normalize, whose SSE2 code starts from the CPU specific rsqrtss estimate
+// (external/rtm/includes/rtm/quatf.h:917-953) and cannot be reproduced bit for bit by anyone: the IEEE 1 / sqrt stands in for it (the
+// tests' CPU restatement has both flavours; errors agree with the reference within 5e-5 on poses tens of units across,
+// tests/test_gpu_error_metric.py). The matrix metric never normalises: it is bit-identical to the reference itself.
 #include "context.h"
 
 #include <algorithm>

@@ -32,7 +32,7 @@ extern "C" {
 #endif
 
 #define ACLB200_VERSION_MAJOR 0
-#define ACLB200_VERSION_MINOR 2
+#define ACLB200_VERSION_MINOR 3
 
 typedef enum aclb200_status
 {
