@@ -99,7 +99,7 @@ namespace aclb200
 		};
 
 		// Validates one blob and appends its clip image to `data`. Returns an empty string on success, else why the clip is
-		// rejected; `unsupported` tells apart valid ACL data we refuse (database clips) from invalid buffers.
+		// rejected; `unsupported` tells apart valid ACL data we refuse (unknown track types, images past 4 GiB) from invalid buffers.
 		std::string transcode_clip(const uint8_t* blob, uint32_t size, bool check_hash, std::vector<uint8_t>& data, parse_result& out, bool& unsupported)
 		{
 			unsupported = false;
@@ -253,12 +253,18 @@ namespace aclb200
 			const uint32_t translation_format = (misc >> 3) & 1;
 			const uint32_t rotation_format = (misc >> 4) & 15;
 			const bool has_database = ((misc >> 8) & 1) != 0;
-			const bool has_stripped = ((misc >> 10) & 1) != 0;
+			// A clip bound to a streaming database is decoded from the key frames that stay resident in the clip: what
+			// decompression_context<settings with database support>::initialize(tracks) gives with no database bound, and with a database
+			// none of whose tiers is streamed in (decompress.impl.h:67-83; seek_v0 treats it as a clip with stripped key frames,
+			// decompression.transform.h:262-265). Tier streaming is not implemented. Its transform header names the database metadata
+			// (compressed_headers.h:245-246): the flag without that header is a corrupt clip.
 			if (has_database)
 			{
-				unsupported = true;
-				return "clips bound to a streaming database are not supported";
+				const uint32_t database_header_offset = rd_u32(blob + k_type_header_offset + 32);
+				if (database_header_offset == 0xFFFFFFFFu || !in_bounds(k_type_header_offset + database_header_offset, 8))
+					return "database flag without a database header";
 			}
+			const bool has_stripped = ((misc >> 10) & 1) != 0 || has_database;
 			if (rotation_format != k_rot_full && rotation_format != k_rot_drop_w_full && rotation_format != k_rot_drop_w_variable)
 				return "invalid rotation format";
 

@@ -140,7 +140,7 @@ static int view_clip(const void* blob, clip_view* v)
 int aclo_validate(const void* blob, size_t size, int check_hash)
 {
 	/* compressed_tracks::is_valid, core/impl/compressed_tracks.impl.h:278-301, then
-	 * decompression_version_selector::is_version_supported and our own "no database" rule */
+	 * decompression_version_selector::is_version_supported */
 	if (blob == NULL || size < 32)
 		return -1;
 	if (((uintptr_t)blob & 15u) != 0)
@@ -162,7 +162,13 @@ int aclo_validate(const void* blob, size_t size, int check_hash)
 			return -7;
 	}
 	if (p[15] == ACLO_TRACK_QVVF && ((rd_u32(p + 28) >> 8) & 1))
-		return -8;											/* database clips are rejected */
+	{
+		/* A clip bound to a database decodes from the key frames resident in the clip, like a context initialised without
+		 * its database (decompress.impl.h:67-83). Its transform header names the database metadata (compressed_headers.h:245-246): a
+		 * flag without that header is a corrupt clip. */
+		if (stored_size < 32 + 52 || rd_u32(p + 32 + 32) == ACLO_INVALID_OFFSET || rd_u32(p + 32 + 32) >= stored_size - 32)
+			return -8;
+	}
 	return 0;
 }
 
@@ -320,8 +326,8 @@ static void segment_data_offsets(const clip_view* v, uint32_t segment_header_off
 int aclo_transform_seek(const void* blob, const aclo_settings* settings, float sample_time,
 	uint32_t rounding_policy, uint32_t looping_policy, aclo_seek_state* st)
 {
-	/* seek_v0, decompression/impl/decompression.transform.h:206-563 (database branches removed: clips
-	 * with a database are rejected by aclo_validate) */
+	/* seek_v0, decompression/impl/decompression.transform.h:206-563 with no database bound (db == nullptr: the tier metadata branches
+	 * :289-305,326-353 fall away, a database clip is sought like a clip with stripped key frames, :262-265) */
 	clip_view v;
 	if (view_clip(blob, &v) != 0 || v.track_type != ACLO_TRACK_QVVF)
 		return -1;
@@ -352,7 +358,7 @@ int aclo_transform_seek(const void* blob, const aclo_settings* settings, float s
 
 	if (v.num_segments == 1)
 	{
-		if (v.has_stripped_keyframes)
+		if (v.has_stripped_keyframes || v.has_database)
 		{
 			/* :272-362 */
 			const uint32_t sample_indices0 = rd_u32(v.th + headers + 16);
@@ -397,7 +403,7 @@ int aclo_transform_seek(const void* blob, const aclo_settings* settings, float s
 		segment_key_frame0 = key_frame0 - start0;
 		segment_key_frame1 = key_frame1 - start1;
 
-		if (v.has_stripped_keyframes)
+		if (v.has_stripped_keyframes || v.has_database)
 		{
 			/* :411-515 */
 			const uint32_t sample_indices0 = rd_u32(v.th + headers + hsize * segment_index0 + 16);

@@ -429,3 +429,29 @@ def transform_error_matrix(spec: TransformSpec, blob: np.ndarray) -> dict:
     if rc != 0:
         raise RuntimeError(f"aclref_transform_error_matrix failed ({rc})")
     return dict(index=int(result.index), error=float(result.error), sample_time=float(result.sample_time), errors=errors)
+
+
+def compress_transform_database(spec: TransformSpec, medium_proportion: float = 0.0, low_proportion: float = 0.5) -> np.ndarray:
+    """The raw clip of `spec` compressed with database support and split by acl::build_database: returns the compressed_tracks blob bound
+    to the database (its movable key frames moved out; the database itself is dropped)."""
+    c_spec = spec.to_c()
+    ptr, size = C.c_void_p(), C.c_uint32()
+    fn = lib().aclref_compress_transform_database
+    fn.argtypes = [C.POINTER(_TransformSpec), C.c_float, C.c_float, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]
+    rc = fn(C.byref(c_spec), medium_proportion, low_proportion, C.byref(ptr), C.byref(size))
+    if rc != 0:
+        raise RuntimeError(f"reference database compression failed ({rc}) for {spec}")
+    return _take(ptr, size.value)
+
+
+def decompress_tracks_without_database(blob: np.ndarray, t: float, rounding: int = ROUND_NONE, looping: int = LOOP_AS_COMPRESSED,
+                                       writer: int = WRITER_LEGACY) -> np.ndarray:
+    """decompression_context<debug settings + database support>::initialize(tracks) with NO database bound, seek, decompress_tracks."""
+    n = num_tracks_of(blob)
+    out = np.zeros((n, 12), dtype=np.float32)
+    fn = lib().aclref_decompress_tracks_without_database
+    fn.argtypes = [C.c_void_p, C.c_float, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+    rc = fn(blob.ctypes.data, t, rounding, looping, writer, out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"reference decompress_tracks (database clip, no database) failed ({rc})")
+    return out

@@ -23,6 +23,7 @@
 #include <acl/compression/track_error.h>
 #include <acl/compression/transform_error_metrics.h>
 #include <acl/decompression/decompress.h>
+#include <acl/decompression/database/database.h>
 
 #include <atomic>
 #include <chrono>
@@ -373,6 +374,11 @@ namespace
 
 	// kind 1: everything enabled (all formats, always normalize, per track rounding)
 	using settings_debug = debug_transform_decompression_settings;
+	// debug settings + database support (decompression_settings.h:163-165): what a context needs to accept a clip bound to a database
+	struct settings_database final : public debug_transform_decompression_settings
+	{
+		using database_settings_type = default_database_settings;
+	};
 
 	// kind 2: what tools/acl_decompressor/sources/benchmark.cpp:94-101 times
 	struct settings_benchmark final : public default_transform_decompression_settings
@@ -1197,6 +1203,83 @@ extern "C"
 			}
 		}
 		return 0;
+	}
+
+	//////////////////////////////////////////////////////////////////////////
+	// SURVEY 8(f2), first step: clips bound to a streaming database, decoded from the key frames that stay resident in the clip
+
+	// Compresses the raw clip of `spec` with database support (compress_track_list with enable_database_support, compress.transform.impl.h:158-166)
+	// and splits it with acl::build_database (compress.h:86-100; `medium` / `low` = compression_database_settings proportions): the returned
+	// blob is the compressed_tracks instance BOUND TO THE DATABASE (has_database, the movable key frames moved out). The database itself is
+	// dropped: these clips are decoded without it.
+	int aclref_compress_transform_database(const aclref_transform_spec* spec, float medium_proportion, float low_proportion, void** out_blob, uint32_t* out_size)
+	{
+		iallocator& alloc = allocator();
+		track_array_qvvf track_list(alloc, spec->num_tracks);
+		make_transform_tracks(*spec, track_list);
+
+		qvvf_transform_error_metric error_metric;
+		compression_settings settings;
+		settings.level = static_cast<compression_level8>(spec->level);
+		settings.rotation_format = static_cast<rotation_format8>(spec->rotation_format);
+		settings.translation_format = static_cast<vector_format8>(spec->translation_format);
+		settings.scale_format = static_cast<vector_format8>(spec->scale_format);
+		settings.error_metric = &error_metric;
+		settings.optimize_loops = spec->optimize_loops != 0;
+		settings.enable_database_support = true;
+
+		compressed_tracks* tracks = nullptr;
+		output_stats stats;
+		error_result result = compress_track_list(alloc, track_list, settings, tracks, stats);
+		if (result.any() || tracks == nullptr)
+		{
+			fprintf(stderr, "aclref_compress_transform_database: %s\n", result.any() ? result.c_str() : "no output");
+			return -1;
+		}
+
+		compression_database_settings database_settings;
+		database_settings.medium_importance_tier_proportion = medium_proportion;
+		database_settings.low_importance_tier_proportion = low_proportion;
+		const compressed_tracks* input_list[1] = { tracks };
+		compressed_tracks* bound_list[1] = { nullptr };
+		compressed_database* database = nullptr;
+		result = build_database(alloc, database_settings, input_list, 1, bound_list, database);
+		alloc.deallocate(tracks, tracks->get_size());
+		if (result.any() || bound_list[0] == nullptr)
+		{
+			fprintf(stderr, "aclref_compress_transform_database: build_database: %s\n", result.any() ? result.c_str() : "no output");
+			return -2;
+		}
+		if (database != nullptr)
+			alloc.deallocate(database, database->get_size());
+
+		const uint32_t size = bound_list[0]->get_size();
+		void* copy = nullptr;
+		if (posix_memalign(&copy, 64, size + 64) != 0)
+			return -3;
+		std::memcpy(copy, bound_list[0], size);
+		std::memset(static_cast<uint8_t*>(copy) + size, 0, 64);
+		alloc.deallocate(bound_list[0], size);
+		*out_blob = copy;
+		*out_size = size;
+		return 0;
+	}
+
+	// decompression_context<settings with database support>::initialize(tracks) -- NO database bound (decompress.impl.h:67-83: database =
+	// nullptr) -- then seek + decompress_tracks: what a database clip gives before any tier is streamed in. writer_mode as aclref_decompress_tracks.
+	int aclref_decompress_tracks_without_database(const void* blob, float sample_time, uint32_t rounding, uint32_t looping, uint32_t writer_mode, float* out)
+	{
+		decode_args args;
+		args.tracks = static_cast<const compressed_tracks*>(blob);
+		args.sample_time = sample_time;
+		args.rounding = static_cast<sample_rounding_policy>(rounding);
+		args.looping = static_cast<sample_looping_policy>(looping);
+		args.track_index = -1;
+		args.out = out;
+		args.per_track_rounding = nullptr;
+		args.constant_defaults = nullptr;
+		args.variable_defaults = nullptr;
+		return decode_dispatch_writer<settings_database>(writer_mode, args);
 	}
 
 	// The scalar flavour: calculate_compression_error(allocator, raw_tracks, context) (track_error.impl.h:400-463 -> calculate_scalar_track_error

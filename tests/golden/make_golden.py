@@ -97,8 +97,28 @@ def make_scalar(name: str, spec) -> None:
     np.savez_compressed(clips.golden_path(name, "golden.npz"), times=times, values=values)
 
 
+# clips bound to a streaming database (acl::build_database), decoded by the reference WITHOUT the database (first step)
+DATABASE_GOLDEN = {"database_c1_30bones": ("c1_30bones", 0.0, 0.5), "database_mixed_scale": ("mixed_scale", 0.3, 0.3)}
+
+
+def make_database(golden_name: str, clip_name: str, medium: float, low: float) -> None:
+    spec = clips.TRANSFORM_SPECS[clip_name]
+    blob = ref.compress_transform_database(spec, medium, low)
+    with open(clips.golden_path(golden_name, "acl.bin"), "wb") as f:
+        f.write(blob.tobytes())
+    times = clips.sample_times(spec)
+    poses = np.zeros((4, len(times), spec.num_tracks, 10), dtype=np.float32)
+    for rounding in range(4):
+        for ti, t in enumerate(times):
+            poses[rounding, ti] = ref.decompress_tracks_without_database(blob, float(t), rounding)[:, clips.DEFINED_LANES]
+    np.savez_compressed(clips.golden_path(golden_name, "golden.npz"), times=times, poses=poses)
+
+
 def main() -> None:
     os.makedirs(clips.GOLDEN_DIR, exist_ok=True)
+    for golden_name, (clip_name, medium, low) in DATABASE_GOLDEN.items():
+        make_database(golden_name, clip_name, medium, low)
+        print("database", golden_name)
     for name, spec in clips.TRANSFORM_SPECS.items():
         make_transform(name, spec)
         print("transform", name)

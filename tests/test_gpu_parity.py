@@ -330,7 +330,7 @@ def test_host_buffer_api_matches_device_api(gpu):
 
 
 def test_upload_rejects_what_initialize_rejects(gpu):
-    """decompression_context::initialize() returns false for these (decompress.impl.h:66-83); database clips are refused by design."""
+    """decompression_context::initialize() returns false for these (decompress.impl.h:66-83)."""
     ab, ctx = gpu["ab"], gpu["ctx"]
     from oracle import ref
     good = clips.load_blob("c1_30bones")
@@ -353,11 +353,51 @@ def test_upload_rejects_what_initialize_rejects(gpu):
     assert status_of(ref.aligned_blob(bad), True) == 2      # hash
     assert status_of(ref.aligned_blob(bad), False) == 0
     bad = good.copy(); bad[29] |= 1
-    assert status_of(ref.aligned_blob(bad)) == 3            # database clip: unsupported
+    assert status_of(ref.aligned_blob(bad)) == 2            # database flag without a database header: corrupt
     assert status_of(ref.aligned_blob(good[:200].copy())) == 2      # truncated
     with pytest.raises(ab.AclB200Error) as err:
         ctx.upload([good, clips.load_blob("float1")])
     assert err.value.status == 3                            # mixed track types
+
+
+@pytest.mark.parametrize("golden_name", ["database_c1_30bones", "database_mixed_scale"])
+def test_database_clips_decode_from_their_resident_key_frames(gpu, golden_name):
+    """SURVEY 8(f2), first step: clips bound to a streaming database (acl::build_database moved their movable key frames out) are accepted
+    and decoded from the key frames that stay in the clip, like decompression_context<settings with database support>::initialize(tracks)
+    with no database bound (decompress.impl.h:67-83): bit for bit against the reference's own output (golden) and the oracle, in the same
+    launch as an ordinary clip, through the pipeline kernel and through decompress_track."""
+    torch, ab, ctx, port = gpu["torch"], gpu["ab"], gpu["ctx"], gpu["port"]
+    blob = clips.load_blob(golden_name)
+    other = clips.load_blob("ragged_17")
+    g = np.load(clips.golden_path(golden_name, "golden.npz"))
+    clipset = ctx.upload([other, blob], check_hash=True)
+    n = port.num_tracks_of(blob)
+    times = g["times"]
+    settings = port.settings_for_kind(1)
+    req_clip = np.concatenate([np.ones(len(times), np.uint32), np.zeros(4, np.uint32)])
+    req_time = np.concatenate([times, np.array([0.0, 0.4, 0.9, 1.3], np.float32)])
+    for rounding in range(4):
+        got = _decode(gpu, clipset, req_clip, req_time, _options(gpu, settings, rounding_policy=rounding))
+        for i, t in enumerate(times):
+            assert clips.bit_equal(got[i, :n][:, LANES], g["poses"][rounding, i]), (golden_name, rounding, float(t))
+        for looping in (ab.LOOP_CLAMP, ab.LOOP_WRAP):
+            got = _decode(gpu, clipset, req_clip, req_time, _options(gpu, settings, rounding_policy=rounding, looping_policy=looping))
+            for i, t in enumerate(times):
+                want = port.transform_decompress_tracks(blob, settings, float(t), rounding, looping)
+                assert clips.bit_equal(got[i, :n][:, LANES], want[:, LANES]), (golden_name, rounding, looping, float(t))
+    # decompress_track: vectors bit-exact, rotations within the single track tolerance
+    bones = np.array([0, n // 2, n - 1], dtype=np.uint32)
+    for bone in bones:
+        requests = ab.make_requests(np.ones(len(times), np.uint32), times)
+        d_out = torch.zeros((len(times), 12), dtype=torch.float32, device="cuda")
+        ctx.decompress_track(clipset, _to_device(gpu, requests), _to_device(gpu, np.full(len(times), bone, np.uint32)), len(times), _options(gpu, settings), d_out)
+        torch.cuda.synchronize()
+        single = d_out.cpu().numpy()
+        for i, t in enumerate(times):
+            want = port.transform_decompress_tracks(blob, settings, float(t), 0)[bone]
+            assert np.max(np.abs(single[i, :4] - want[:4])) <= SINGLE_TRACK_TOLERANCE, (golden_name, bone, float(t))
+            assert clips.bit_equal(single[i, [4, 5, 6, 8, 9, 10]], want[[4, 5, 6, 8, 9, 10]]), (golden_name, bone, float(t))
+    clipset.release()
 
 
 FAST_MATH_TOLERANCE = 1e-5      # BASELINE.json north star: "within 1e-5 on the float QVV components"

@@ -185,5 +185,40 @@ def test_validate_rejects_bad_buffers(oracle_port):
     bad = blob.copy(); bad[200] ^= 0x01                     # payload bit flip -> hash mismatch only
     assert oracle_port.validate(clips.ref.aligned_blob(bad), False) == 0
     assert oracle_port.validate(clips.ref.aligned_blob(bad), True) != 0
-    bad = blob.copy(); bad[29] |= 0x01                      # has_database
+    bad = blob.copy(); bad[29] |= 0x01                      # has_database without a database header: corrupt
     assert oracle_port.validate(clips.ref.aligned_blob(bad), False) != 0
+
+
+DATABASE_CASES = [("c1_30bones", 0.0, 0.5), ("c2_100bones", 0.25, 0.5), ("mixed_scale", 0.3, 0.3), ("looping", 0.0, 0.75), ("single_segment", 0.5, 0.25)]
+
+
+@pytest.mark.parametrize("name,medium,low", DATABASE_CASES)
+def test_port_decodes_database_clips_like_a_context_without_its_database(reference, oracle_port, name, medium, low):
+    """SURVEY 8(f2), first step: a clip bound to a streaming database (acl::build_database moved its movable key frames out) decodes from the
+    key frames that stay resident, exactly like decompression_context<settings with database support>::initialize(tracks) with no database
+    bound (decompress.impl.h:67-83, decompression.transform.h:262-265). Bit for bit, every rounding and looping policy."""
+    spec = clips.TRANSFORM_SPECS[name]
+    blob = reference.compress_transform_database(spec, medium, low)
+    assert (int(blob[28:32].view(np.uint32)[0]) >> 8) & 1 == 1
+    assert blob.size < clips.load_blob(name).size               # key frames really left the clip
+    assert oracle_port.validate(blob, True) == 0
+    settings = _settings(1)
+    for looping in (0, 1, 2):
+        for rounding in (0, 1, 2, 3):
+            for t in clips.sample_times(spec):
+                want = reference.decompress_tracks_without_database(blob, float(t), rounding, looping)
+                got = oracle_port.transform_decompress_tracks(blob, settings, float(t), rounding, looping)
+                assert clips.bit_equal(got[:, LANES], want[:, LANES]), (name, looping, rounding, float(t))
+
+
+@pytest.mark.parametrize("golden_name", ["database_c1_30bones", "database_mixed_scale"])
+def test_port_matches_golden_database_clips(oracle_port, golden_name):
+    """The committed database clips (tests/golden/make_golden.py) and what the reference decoded from them without their database."""
+    blob = clips.load_blob(golden_name)
+    assert oracle_port.validate(blob, True) == 0
+    g = np.load(clips.golden_path(golden_name, "golden.npz"))
+    settings = _settings(1)
+    for rounding in range(4):
+        for ti, t in enumerate(g["times"]):
+            got = oracle_port.transform_decompress_tracks(blob, settings, float(t), rounding)[:, LANES]
+            assert clips.bit_equal(got, g["poses"][rounding, ti]), (golden_name, rounding, float(t))
