@@ -20,7 +20,8 @@
 //     namespace acl_b200 (float4 instead of the rtm types).
 //
 // Semantics kept (decompress.impl.h:66-260): initialize() returns false for an invalid / unsupported buffer, for a track type,
-// version or rotation / translation / scale format the settings do not support, and for database bound clips; relocated() and
+// version or rotation / translation / scale format the settings do not support (a clip bound to a streaming database is accepted and
+// decodes from its resident key frames, like a reference context initialised without its database); relocated() and
 // is_bound_to() compare the hash (decompression.transform.h:134-176); seek() on an unbound context and decompress_*() before a
 // seek() do nothing; transform AND scalar clips (write_float1..4 / write_vector4); every sample_rounding_policy including per_track
 // (writer.get_rounding_policy per track); all default sub-track modes; skip_all_* / skip_track_*.

@@ -39,7 +39,7 @@ typedef enum aclb200_status
 	ACLB200_OK = 0,
 	ACLB200_ERR_INVALID_ARGUMENT = 1,
 	ACLB200_ERR_INVALID_CLIP = 2,		/* what decompression_context::initialize() reports by returning false (decompress.impl.h:66-83) */
-	ACLB200_ERR_UNSUPPORTED = 3,		/* valid ACL data this build refuses: database clips, mixed track types in one clip set */
+	ACLB200_ERR_UNSUPPORTED = 3,		/* valid ACL data this build refuses: mixed track types in one clip set, clip images past 4 GiB */
 	ACLB200_ERR_NO_DEVICE = 4,
 	ACLB200_ERR_CUDA = 5,
 	ACLB200_ERR_OUT_OF_MEMORY = 6
@@ -185,10 +185,13 @@ ACLB200_API const char* aclb200_last_error(const aclb200_context* context);
 
 /* Replaces decompression_context::initialize(const compressed_tracks&) (decompress.h:90-101,
  * decompress.impl.h:66-83) for `num_clips` clips at once: validates every blob exactly like
- * compressed_tracks::is_valid(check_hash) + is_version_supported (v02_00_00 .. v02_01_00), rejects database
- * clips, copies the blobs to device memory (>= 64 bytes of tail slack for the `_unsafe` unaligned reads,
+ * compressed_tracks::is_valid(check_hash) + is_version_supported (v02_00_00 .. v02_01_00), copies the blobs to device memory (>= 64 bytes of tail slack for the `_unsafe` unaligned reads,
  * compress.transform.impl.h:387-396) and builds the acceleration index. Synchronous; the host blobs may be
- * freed when it returns. `out_failed_clip` (optional) receives the index of the first rejected clip. */
+ * freed when it returns. `out_failed_clip` (optional) receives the index of the first rejected clip.
+ * A clip bound to a streaming database (compressed_tracks::has_database, what acl::build_database returns) is accepted and decodes from
+ * the key frames that stay resident in the clip: what decompression_context<settings with database support>::initialize(tracks) gives
+ * with no database bound, or with a database none of whose tiers is streamed in (decompress.impl.h:67-83, decompression.transform.h:
+ * 262-265). Streaming the medium / low importance tiers in is not implemented. */
 ACLB200_API aclb200_status aclb200_upload_clips(aclb200_context* context, const void* const* blobs, const uint32_t* sizes, uint32_t num_clips,
 	uint32_t check_hash, aclb200_clipset** out_clipset, uint32_t* out_failed_clip);
 
