@@ -29,6 +29,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <type_traits>
 #include <vector>
 
@@ -983,7 +984,7 @@ extern "C"
 		return check_cuda(context, error, "local_to_object_space");
 	}
 
-	aclb200_status aclb200_calculate_compression_error(aclb200_context* context, const aclb200_clipset* clipset, const aclb200_error_job* jobs,
+	static aclb200_status calculate_compression_error_impl(aclb200_context* context, const aclb200_clipset* clipset, const aclb200_error_job* jobs,
 		uint32_t num_jobs, const void* d_raw_poses, const uint32_t* d_parent_indices, const float* d_shell_distances,
 		const uint32_t* d_output_indices, const void* d_base_poses, const aclb200_options* options, aclb200_track_error* d_out_errors,
 		float* d_out_error_matrix, void* stream)
@@ -1204,7 +1205,24 @@ extern "C"
 		return check_cuda(context, error, "calculate_compression_error");
 	}
 
-	aclb200_status aclb200_decompress_all_samples(aclb200_context* context, const aclb200_clipset* clipset, const aclb200_error_job* jobs,
+	// nothing may unwind through the extern "C" boundary: the job tables are host allocations
+	aclb200_status aclb200_calculate_compression_error(aclb200_context* context, const aclb200_clipset* clipset, const aclb200_error_job* jobs,
+		uint32_t num_jobs, const void* d_raw_poses, const uint32_t* d_parent_indices, const float* d_shell_distances,
+		const uint32_t* d_output_indices, const void* d_base_poses, const aclb200_options* options, aclb200_track_error* d_out_errors,
+		float* d_out_error_matrix, void* stream)
+	{
+		try
+		{
+			return calculate_compression_error_impl(context, clipset, jobs, num_jobs, d_raw_poses, d_parent_indices, d_shell_distances, d_output_indices,
+				d_base_poses, options, d_out_errors, d_out_error_matrix, stream);
+		}
+		catch (const std::exception&)
+		{
+			return set_error(context, ACLB200_ERR_OUT_OF_MEMORY, "calculate_compression_error: out of host memory for the job tables");
+		}
+	}
+
+	static aclb200_status decompress_all_samples_impl(aclb200_context* context, const aclb200_clipset* clipset, const aclb200_error_job* jobs,
 		uint32_t num_jobs, const aclb200_options* options, void* d_out, void* stream)
 	{
 		if (context == nullptr || clipset == nullptr || options == nullptr)
@@ -1265,6 +1283,19 @@ extern "C"
 		return clipset->info.track_type == ACLB200_TRACK_QVVF
 			? aclb200_decompress_tracks(context, clipset, p.requests, p.num_poses, options, d_out, stream)
 			: aclb200_scalar_decompress_tracks(context, clipset, p.requests, p.num_poses, options, d_out, stream);
+	}
+
+	aclb200_status aclb200_decompress_all_samples(aclb200_context* context, const aclb200_clipset* clipset, const aclb200_error_job* jobs,
+		uint32_t num_jobs, const aclb200_options* options, void* d_out, void* stream)
+	{
+		try
+		{
+			return decompress_all_samples_impl(context, clipset, jobs, num_jobs, options, d_out, stream);
+		}
+		catch (const std::exception&)
+		{
+			return set_error(context, ACLB200_ERR_OUT_OF_MEMORY, "decompress_all_samples: out of host memory for the job table");
+		}
 	}
 
 	aclb200_status aclb200_set_error_chunk_bytes(aclb200_context* context, uint64_t bytes)
