@@ -57,6 +57,45 @@ def route_requests(req_clip, req_time, owner, local_index, rank: int):
     return mine, local.astype(np.uint32), req_time[mine]
 
 
+def route_error_jobs(jobs, owner, local_index, rank: int):
+    """The compression error jobs (aclb200_error_job records, one per clip to measure: SURVEY 8 f1) rank `rank` runs: the measurement of a
+    clip needs nothing but the clip, its raw poses and its skeleton, so it shards with the clips like the decode does. Returns (positions
+    in the global job list, the jobs with `clip` rewritten to the index inside the rank's clip set). Raw pose / skeleton offsets are left
+    as they are: they index whatever the rank holds in its own device buffers, which the caller lays out per rank."""
+    jobs = np.asarray(jobs)
+    job_clip = jobs["clip"].astype(np.int64)
+    if np.any(job_clip >= len(owner)):
+        raise ValueError("an error job names a clip outside the clip table")
+    mine = np.nonzero(owner[job_clip] == rank)[0]
+    routed = jobs[mine].copy()
+    routed["clip"] = local_index[job_clip[mine]]
+    return mine, routed
+
+
+def reduce_worst_error(errors_this_rank, positions_this_rank, num_jobs: int, device=None):
+    """Every rank's per job (index, error, sample_time, flags) records gathered into the global job order (one all_reduce of a table that
+    is zero outside the rank's own jobs: jobs are disjoint across ranks)."""
+    import torch
+    import torch.distributed as dist
+    table = np.zeros((num_jobs, 4), dtype=np.float64)
+    records = np.asarray(errors_this_rank)
+    if len(positions_this_rank):
+        table[positions_this_rank, 0] = records["index"].astype(np.float64) + 1.0      # 0 = not this rank's job; 0xFFFFFFFF + 1 stays exact in f64
+        table[positions_this_rank, 1] = records["error"]
+        table[positions_this_rank, 2] = records["sample_time"]
+        table[positions_this_rank, 3] = records["flags"]
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.from_numpy(table).to(device) if device is not None else torch.from_numpy(table)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        table = t.cpu().numpy()
+    out = np.zeros(num_jobs, dtype=np.dtype([("index", np.uint32), ("error", np.float32), ("sample_time", np.float32), ("flags", np.uint32)]))
+    out["index"] = (table[:, 0] - 1.0).astype(np.int64).astype(np.uint32)
+    out["error"] = table[:, 1]
+    out["sample_time"] = table[:, 2]
+    out["flags"] = table[:, 3].astype(np.uint32)
+    return out
+
+
 def exchange_plan(generated_bounds, owner_bounds, sizes):
     """Bytes every rank sends to every other rank when clips generated (or loaded) by contiguous ranges `generated_bounds` move to
     the owners `owner_bounds` picked by partition_clips: plan[src][dst] = (first clip, last clip + 1, bytes). Both partitions are

@@ -183,3 +183,77 @@ def test_partition_and_routing_properties():
         assert sorted(seen) == list(range(len(picks)))
 
     check()
+
+
+def _error_job_worker(rank, world, port, result_path):
+    """SURVEY 8(f1) at N > 1: the compression error jobs follow their clips; every rank measures its own (here with the oracle's IEEE
+    flavour as the stand-in for the device call), one all_reduce puts the per clip records in the global job order."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import port as oracle_port, ref
+        from acl_b200.api import ERROR_JOB_DTYPE
+        names = ["c1_30bones", "mixed_scale", "single_segment", "ragged_17", "one_bone"]
+        blobs = [clips.load_blob(n) for n in names]
+        owner, local, bounds = sharding.partition_clips([b.nbytes for b in blobs], world)
+        order = [3, 0, 4, 1, 2, 0]          # one clip measured twice
+        jobs = np.zeros(len(order), dtype=ERROR_JOB_DTYPE)
+        cases = {}
+        for slot, clip in enumerate(order):
+            g = np.load(clips.golden_path(names[clip], "error.npz"))
+            cases[clip] = g
+            jobs[slot]["clip"] = clip
+            jobs[slot]["num_samples"] = g["raw_poses"].shape[0]
+            jobs[slot]["num_tracks"] = g["raw_poses"].shape[1]
+            jobs[slot]["sample_rate"] = float(g["sample_rate"])
+            jobs[slot]["duration"] = float(g["duration"])
+        positions, routed = sharding.route_error_jobs(jobs, owner, local, rank)
+        lo, hi = bounds[rank]
+        records = np.zeros(len(routed), dtype=np.dtype([("index", np.uint32), ("error", np.float32), ("sample_time", np.float32), ("flags", np.uint32)]))
+        from tests.test_error_metric_oracle import lossy_poses_from_port
+        for i, job in enumerate(routed):
+            clip = lo + int(job["clip"])                 # the rank's clip set is the slice bounds[rank] of the table
+            assert owner[clip] == rank
+            g = cases[clip]
+            lossy = lossy_poses_from_port(blobs[clip], 1, int(job["num_samples"]), float(job["sample_rate"]), float(job["duration"]), int(g["rounding"]))
+            got, _, _ = oracle_port.transform_track_error(g["raw_poses"], lossy, float(job["sample_rate"]), float(job["duration"]), g["parents"],
+                                                          g["shell_distances"], oracle_port.NORMALIZE_IEEE)
+            records[i] = (got.index, got.error, got.sample_time, 0)
+        merged = sharding.reduce_worst_error(records, positions, len(jobs))
+        if rank == 0:
+            ok = True
+            for slot, clip in enumerate(order):
+                g = cases[clip]
+                ok &= abs(float(merged[slot]["error"]) - float(g["error"])) <= 5e-5 and int(merged[slot]["index"]) == int(g["index"])
+            np.save(result_path, np.array([1.0 if ok else 0.0, float(len(merged))]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_error_jobs_follow_their_clips(tmp_path):
+    if not all(os.path.exists(clips.golden_path(n, "error.npz")) for n in ["c1_30bones", "mixed_scale", "single_segment", "ragged_17", "one_bone"]):
+        pytest.skip("golden error files missing")
+    world = 2
+    result_path = str(tmp_path / "result.npy")
+    mp.spawn(_error_job_worker, args=(world, _free_port(), result_path), nprocs=world, join=True)
+    ok, total = np.load(result_path)
+    assert ok == 1.0 and total == 6
+
+
+def test_route_error_jobs_partitions_the_job_list():
+    from acl_b200.api import ERROR_JOB_DTYPE
+    owner, local, bounds = sharding.partition_clips([5, 5, 5, 5, 5], 2)
+    jobs = np.zeros(7, dtype=ERROR_JOB_DTYPE)
+    jobs["clip"] = [4, 0, 2, 1, 3, 0, 4]
+    jobs["num_samples"] = np.arange(7) + 10
+    seen = []
+    for rank in range(2):
+        positions, routed = sharding.route_error_jobs(jobs, owner, local, rank)
+        seen += list(positions)
+        for p, job in zip(positions, routed):
+            assert owner[jobs[p]["clip"]] == rank and job["clip"] == local[jobs[p]["clip"]] and job["num_samples"] == jobs[p]["num_samples"]
+    assert sorted(seen) == list(range(7))
+    jobs["clip"][0] = 9
+    with pytest.raises(ValueError):
+        sharding.route_error_jobs(jobs, owner, local, 0)
