@@ -1808,3 +1808,15 @@ int aclo_scalar_track_error(const float* raw_values, const float* lossy_values, 
 	}
 	return 0;
 }
+
+/* Test hooks for the known-answer table of the reference's own math tests (external/rtm/tests/sources/test_qvv.cpp:225-257):
+ * rtm::qvv_mul (either branch) and rtm::qvv_mul_point3 as restated above. */
+void aclo_test_qvv_mul(const float* lhs, const float* rhs, int normalize_mode, float* out)
+{
+	qvv_mul_plain(lhs, rhs, normalize_mode, out);
+}
+
+void aclo_test_qvv_mul_point3(const float* point, const float* qvv, float* out)
+{
+	qvv_mul_point3(point, qvv, out);
+}

@@ -145,6 +145,11 @@ int aclo_apply_additive_to_base(uint32_t additive_format, const float* base_pose
 int aclo_scalar_track_error(const float* raw_values, const float* lossy_values, uint32_t num_samples, uint32_t num_tracks, uint32_t components,
 	float sample_rate, float duration, aclo_track_error* out_error);
 
+/* rtm::qvv_mul / rtm::qvv_mul_point3 as restated for the error metric, exposed for the known-answer table of the reference's own math
+ * tests (external/rtm/tests/sources/test_qvv.cpp:225-257, replayed by tests/test_reference_known_answers.py) */
+void aclo_test_qvv_mul(const float* lhs, const float* rhs, int normalize_mode, float* out);
+void aclo_test_qvv_mul_point3(const float* point, const float* qvv, float* out);
+
 /* Single-threaded timing helper for the "port" CPU baseline: decodes `num_requests` (clip, time)
  * requests with default settings and returns the elapsed seconds. */
 double aclo_bench_transform(const void* const* blobs, const uint32_t* request_clip, const float* request_time,
