@@ -6,8 +6,8 @@
 // acl::calculate_compression_error and once with acl_b200::decompression_context + acl_b200::calculate_compression_error: only the
 // namespace differs.
 //
-// usage: shim_track_error            exit 0 = PASS (errors within 5e-5, same worst track and sample time when the error stands clear
-//                                    of that; scalar clips exact),
+// usage: shim_track_error            exit 0 = PASS (errors within 5e-5 -- a different worst track is a tie within that tolerance --;
+//                                    scalar clips and the matrix metric: exact, same track and sample time),
 //                                    3 = no usable GPU (the library has no CPU fallback), 1 = mismatch
 #include <acl/core/ansi_allocator.h>
 #include <acl/compression/compress.h>
